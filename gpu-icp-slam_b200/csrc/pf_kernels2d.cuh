@@ -1,0 +1,443 @@
+// pf_kernels2d.cuh -- sm_100a kernels of the 2D occupancy-grid particle-filter step.
+//
+// One frame = motion -> score -> extrema -> weights+tile scans -> prefix/Neff -> map update ->
+// resample, all on one stream with no host round trip.  Reference semantics per kernel are cited
+// inline (paths relative to michaelwillett/GPU-ICP-SLAM src/).
+#pragma once
+#include "pf_arith.cuh"
+
+namespace pf {
+
+constexpr int kTile = 1024;            // reduction / scan tile (pfslam order)
+constexpr int kScanThreads = 256;      // 8 warps x 32 lanes x 4 items
+constexpr float kLidarRange = 20.0f;   // kernel.cu:44
+constexpr int kFreeWeight = -1;        // kernel.cu:32
+constexpr int kOccupiedWeight = 4;     // kernel.cu:33
+constexpr int kClamp = 113;            // kernel.cu:518 (1<<7)-15
+
+struct MapGeom {
+    int   w, h;                // map_dim, kernel.cu:120
+    float scale_x, scale_y;
+    float res_x, res_y;
+};
+
+// device-resident per-frame result (mirrors pfslam_frame_result)
+struct FrameResult {
+    float pose[3];
+    int   fit_min, fit_max, best_index;
+    float sum_w, sum_w2, neff;
+    int   resampled, n_free, n_wall, n_slow;
+};
+
+// extrema record exchanged between ranks: 8 words
+struct Extrema {
+    int   fit_min, fit_max, best_gidx;
+    float x, y, th;
+    int   pad0, pad1;
+};
+
+// ---------------------------------------------------------------------------------------------
+// motion: kernel.cu:375-397 ParticleAddNoise; device evaluation order of
+// glm::vec3 noise(distx(e2), disty(e2), distt(e2)) is x, y, theta (read off the reference SASS).
+__global__ void __launch_bounds__(256)
+k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n, int frame,
+         int gidx0)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t st = pf_minstd_seed(pf_seed(frame, gidx0 + i, 0));
+    float nx = pf_normal(st, 0.015f);
+    float ny = pf_normal(st, 0.015f);
+    float nt = pf_normal(st, 0.01f);
+    x[i] = __fadd_rn(x[i], nx);
+    y[i] = __fadd_rn(y[i], ny);
+    th[i] = __fadd_rn(th[i], nt);
+}
+
+__global__ void k_debug_trig(const float *__restrict__ x, long long n, float *__restrict__ c,
+                             float *__restrict__ s)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { c[i] = cosf(x[i]); s[i] = sinf(x[i]); }
+}
+
+__global__ void k_init_beams(float *__restrict__ angle, int n_beams)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_beams) angle[j] = pf_lidar_angle(j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One (particle, beam) evaluation exactly as the reference computes it on the GPU
+// (kernel.cu:182-187, :262-270, :247-251; fused multiply-add and IEEE division per its SASS).
+__device__ __forceinline__ int eval_exact(const int8_t *__restrict__ grid, const MapGeom &g,
+                                          float c0x, float c0y, float px, float py, float pth,
+                                          float angle, float r)
+{
+    float rot = __fadd_rn(angle, pth);
+    float cs = cosf(rot), sn = sinf(rot);
+    float wx = __fmaf_rn(r, cs, px);
+    float wy = __fmaf_rn(r, sn, py);
+    float gx = roundf(__fadd_rn(c0x, __fdiv_rn(wx, g.res_x)));
+    float gy = roundf(__fadd_rn(c0y, __fdiv_rn(wy, g.res_y)));
+    if (gx >= 0.0f && gx < (float)g.w && gy >= 0.0f && gy < (float)g.h)
+        return (int)grid[(int)gx * g.w + (int)gy];
+    return 0;
+}
+
+__device__ __forceinline__ long long extrema_key(int fit, int gidx)
+{
+    return (long long)fit * 4294967296ll + (long long)(0xFFFFFFFFu - (uint32_t)gidx);
+}
+
+// Scoring, exact mode: block = 8 warps, lane = particle (32 particles per block), warp w takes
+// beams j = w, w+8, ...; partial sums meet in shared memory.  Writes fit[] and one partial
+// (min, max-key) record per block for k_extrema.
+__global__ void __launch_bounds__(256)
+k_score_exact(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict__ x,
+              const float *__restrict__ y, const float *__restrict__ th, int n, int gidx0,
+              const float *__restrict__ scan, const float *__restrict__ angle, int n_beams,
+              int *__restrict__ fit, int *__restrict__ blk_min, long long *__restrict__ blk_maxkey)
+{
+    __shared__ int part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
+    const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
+    int acc = 0;
+    if (p < n) {
+        const float px = x[p], py = y[p], pth = th[p];
+        for (int j = warp; j < n_beams; j += 8)
+            acc += eval_exact(grid, g, c0x, c0y, px, py, pth, __ldg(&angle[j]), __ldg(&scan[j]));
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        int s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += part[w][lane];
+        int mn = 0x7fffffff;
+        long long mk = (long long)0x8000000000000000ull;
+        if (p < n) { fit[p] = s; mn = s; mk = extrema_key(s, gidx0 + p); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            long long t = __shfl_xor_sync(0xffffffffu, mk, o);
+            mk = t > mk ? t : mk;
+        }
+        if (lane == 0) { blk_min[blockIdx.x] = mn; blk_maxkey[blockIdx.x] = mk; }
+    }
+}
+
+// thrust::minmax_element (kernel.cu:323-326): min, max and the FIRST arg-max, from the per-block
+// partials; also records the best particle's pose for the exchange.
+__global__ void __launch_bounds__(1024)
+k_extrema(const int *__restrict__ blk_min, const long long *__restrict__ blk_maxkey, int n_blk,
+          const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
+          int gidx0, Extrema *__restrict__ out)
+{
+    __shared__ int smin[32];
+    __shared__ long long smax[32];
+    int mn = 0x7fffffff;
+    long long mk = (long long)0x8000000000000000ull;
+    for (int i = threadIdx.x; i < n_blk; i += blockDim.x) {
+        mn = min(mn, blk_min[i]);
+        long long t = blk_maxkey[i];
+        mk = t > mk ? t : mk;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        long long t = __shfl_xor_sync(0xffffffffu, mk, o);
+        mk = t > mk ? t : mk;
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        for (int w = 1; w < nw; w++) { mn = min(mn, smin[w]); mk = smax[w] > mk ? smax[w] : mk; }
+        int best = (int)(0xFFFFFFFFu - (uint32_t)(mk & 0xFFFFFFFFll));
+        Extrema e;
+        e.fit_min = mn; e.fit_max = (int)(mk >> 32); e.best_gidx = best;
+        e.x = x[best - gidx0]; e.y = y[best - gidx0]; e.th = th[best - gidx0];
+        e.pad0 = 0; e.pad1 = 0;
+        *out = e;
+    }
+}
+
+// combine the per-rank extrema: global min, max, first arg-max and its pose
+__device__ __forceinline__ void reduce_extrema(const Extrema *__restrict__ all, int n_ranks,
+                                               int &gmin, int &gmax, int &best, float pose[3])
+{
+    gmin = all[0].fit_min;
+    long long mk = extrema_key(all[0].fit_max, all[0].best_gidx);
+    int br = 0;
+    for (int r = 1; r < n_ranks; r++) {
+        gmin = min(gmin, all[r].fit_min);
+        long long t = extrema_key(all[r].fit_max, all[r].best_gidx);
+        if (t > mk) { mk = t; br = r; }
+    }
+    gmax = (int)(mk >> 32);
+    best = all[br].best_gidx;
+    pose[0] = all[br].x; pose[1] = all[br].y; pose[2] = all[br].th;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pfslam-order tile scan of 4 items per thread over a 1024 tile (256 threads).  Returns the
+// monotone inclusive values LM[0..3] for this thread's items and the tile total (in all threads).
+// Order: thread sequential -> Kogge-Stone over the warp's 32 thread totals -> sequential over the
+// 8 warp totals -> L = (warp_excl + lane_excl) + thread_incl -> running max (exact).
+__device__ __forceinline__ float tile_scan4(const float e[4], float lm[4], float *s_wtot,
+                                            float *s_wmax)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float s0 = e[0];
+    float s1 = __fadd_rn(s0, e[1]);
+    float s2 = __fadd_rn(s1, e[2]);
+    float s3 = __fadd_rn(s2, e[3]);
+    float v = s3;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = __fadd_rn(v, t);
+    }
+    float lane_excl = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) lane_excl = 0.0f;
+    if (lane == 31) s_wtot[warp] = v;
+    __syncthreads();
+    float wexcl = 0.0f;
+    for (int w = 0; w < warp; w++) wexcl = __fadd_rn(wexcl, s_wtot[w]);
+    float b = __fadd_rn(wexcl, lane_excl);
+    float l0 = __fadd_rn(b, s0), l1 = __fadd_rn(b, s1), l2 = __fadd_rn(b, s2), l3 = __fadd_rn(b, s3);
+    // exclusive running max over earlier threads (values are >= 0; thread-local values ascend)
+    float m = l3;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, m, o);
+        if (lane >= o) m = fmaxf(m, t);
+    }
+    float lane_pm = __shfl_up_sync(0xffffffffu, m, 1);
+    if (lane == 0) lane_pm = 0.0f;
+    if (lane == 31) s_wmax[warp] = m;
+    __syncthreads();
+    float pm = lane_pm;
+    for (int w = 0; w < warp; w++) pm = fmaxf(pm, s_wmax[w]);
+    lm[0] = fmaxf(pm, l0); lm[1] = fmaxf(pm, l1); lm[2] = fmaxf(pm, l2); lm[3] = fmaxf(pm, l3);
+    float total = s_wmax[0];
+    for (int w = 1; w < 8; w++) total = fmaxf(total, s_wmax[w]);
+    __syncthreads();   // s_wtot / s_wmax are reused by the next call
+    return total;
+}
+
+// weights + tile scans.  kernel.cu:287-294 kernUpdateWeights: w = w*((float)fit - min)*c with
+// c = 1/(float)(max-min) when max > min (kernel.cu:329-331); SURVEY Q1: only the first
+// ceil(N/2) particles' new weights persist (kernel.cu:337).  Then the per-tile scans that feed
+// Neff (kernel.cu:456-472) and the resampling CDF (kernel.cu:478).
+// tiles layout: [tsum_w (n_tiles)][tsum_w2 (n_tiles)][lm (n)]
+__global__ void __launch_bounds__(kScanThreads)
+k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__restrict__ fit,
+               float *__restrict__ w, int n, int gidx0, int n_sync, int n_tiles,
+               float *__restrict__ tiles)
+{
+    __shared__ float s_wtot[8], s_wmax[8];
+    int gmin, gmax, best; float pose[3];
+    reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
+    const int rng = gmax - gmin;
+    const float c = rng > 0 ? __fdiv_rn(1.0f, (float)rng) : 1.0f;
+    const float fmin = (float)gmin;
+    const int base = blockIdx.x * kTile + threadIdx.x * 4;
+    float e[4], q[4], lm[4], lm2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int i = base + k;
+        float we = 0.0f;
+        if (i < n) {
+            we = w[i];
+            if (rng > 0) we = __fmul_rn(__fmul_rn(we, __fsub_rn((float)fit[i], fmin)), c);
+            if (gidx0 + i < n_sync) w[i] = we;
+        }
+        e[k] = we;
+        q[k] = __fmul_rn(we, we);
+    }
+    float t2 = tile_scan4(q, lm2, s_wtot, s_wmax);
+    float t1 = tile_scan4(e, lm, s_wtot, s_wmax);
+    float *lm_out = tiles + 2 * n_tiles;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k < n) lm_out[base + k] = lm[k];
+    if (threadIdx.x == 0) { tiles[blockIdx.x] = t1; tiles[n_tiles + blockIdx.x] = t2; }
+}
+
+// global tile prefixes (sequential in global tile order), Neff (kernel.cu:472), the resample
+// decision (kernel.cu:474) and robotPos (kernel.cu:338).  tiles_all: n_ranks blocks of
+// [tsum_w][tsum_w2][lm]; prefix: n_tiles_global+1 floats.
+__global__ void __launch_bounds__(1024)
+k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restrict__ tiles_all,
+         int n_tiles_local, long long tiles_block_floats, int n_global,
+         float *__restrict__ prefix, FrameResult *__restrict__ res)
+{
+    extern __shared__ float s_t[];            // 2 * n_tiles_global
+    const int nt = n_ranks * n_tiles_local;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        int r = t / n_tiles_local, tl = t - r * n_tiles_local;
+        const float *blk = tiles_all + (long long)r * tiles_block_floats;
+        s_t[t] = blk[tl];
+        s_t[nt + t] = blk[n_tiles_local + tl];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float p = 0.0f, p2 = 0.0f;
+        prefix[0] = 0.0f;
+        for (int t = 0; t < nt; t++) {
+            p = __fadd_rn(p, s_t[t]);
+            p2 = __fadd_rn(p2, s_t[nt + t]);
+            prefix[t + 1] = p;
+        }
+        float neff = __fdiv_rn(__fmul_rn(p, p), p2);
+        int gmin, gmax, best; float pose[3];
+        reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
+        res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2];
+        res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
+        res->sum_w = p; res->sum_w2 = p2; res->neff = neff;
+        res->resampled = ((double)neff < 0.7 * (double)n_global) ? 1 : 0;
+    }
+}
+
+// resample: kernel.cu:429-444 kernWeightedSample (seed (Neff, frame, i)), gathering
+// from the pre-resample snapshot pose_all.  The CDF is prefix[tile] + lm[i]; it is
+// monotone, so the two-level binary search returns the reference's linear-scan index.
+__global__ void __launch_bounds__(256)
+k_resample(const FrameResult *__restrict__ res, const float *__restrict__ prefix,
+           const float *__restrict__ tiles_all, int n_tiles_local, long long tiles_block_floats,
+           const float *__restrict__ pose_all, int n_local, int n_global, int gidx0, int frame,
+           float *__restrict__ x, float *__restrict__ y, float *__restrict__ th,
+           float *__restrict__ w)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local || !res->resampled) return;
+    const int nt = (n_global + kTile - 1) / kTile;   // == n_ranks * n_tiles_local when sharded
+    uint32_t st = pf_minstd_seed(pf_seed((int)res->neff, frame, gidx0 + i));
+    uint32_t u = pf_minstd_next(st) - 1u;
+    float rnd = __fmul_rn(__fmul_rn((float)u, 4.656612873077392578125e-10f), res->sum_w);
+    // tile: first t with cdf(last of t) = prefix[t+1] >= rnd
+    int lo = 0, hi = nt;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (rnd > prefix[mid + 1]) lo = mid + 1; else hi = mid; }
+    int src;
+    if (lo >= nt) src = n_global - 1;
+    else {
+        const int r = (lo * kTile) / n_local;
+        const int l0 = lo * kTile - r * n_local;
+        const float *lm = tiles_all + (long long)r * tiles_block_floats + 2 * n_tiles_local + l0;
+        const float pt = prefix[lo];
+        int cnt = min(kTile, n_global - lo * kTile);
+        int a = 0, b = cnt;
+        while (a < b) { int mid = (a + b) >> 1; if (rnd > __fadd_rn(pt, lm[mid])) a = mid + 1; else b = mid; }
+        src = lo * kTile + (a < cnt ? a : cnt - 1);
+    }
+    const int r = src / n_local, l = src - r * n_local;
+    const float *pp = pose_all + (long long)r * 3 * n_local;
+    x[i] = pp[l]; y[i] = pp[n_local + l]; th[i] = pp[2 * n_local + l];
+    w[i] = 1.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// map update.  kernel.cu:551-555 center cell; :524-549 kernGetWalls; :190-240 traceRay;
+// :513-522 kernUpdateMap (-1 once per free cell, then +4 once per wall cell, clamp +-113).
+__device__ __forceinline__ void center_cell(const MapGeom &g, float rx, float ry, int &cx, int &cy)
+{
+    float fx = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, (float)g.w), __fdiv_rn(rx, g.res_x)), __fdiv_rn(g.res_x, 2.0f));
+    float fy = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, (float)g.h), __fdiv_rn(ry, g.res_y)), __fdiv_rn(g.res_y, 2.0f));
+    cx = (int)roundf(fx);
+    cy = (int)roundf(fy);
+}
+
+// hit cell of beam j for the robot pose; false if the beam fails the +-20 m filter
+__device__ __forceinline__ bool beam_hit(const MapGeom &g, const float *pose, int cx, int cy,
+                                         float angle, float r, float &wx, float &wy)
+{
+    float rot = __fadd_rn(angle, pose[2]);
+    wx = __fmul_rn(r, cosf(rot));
+    wy = __fmul_rn(r, sinf(rot));
+    if (!(fabsf(wx) < kLidarRange && fabsf(wy) < kLidarRange)) return false;
+    wx = __fadd_rn(roundf(__fdiv_rn(wx, g.res_x)), (float)cx);
+    wy = __fadd_rn(roundf(__fdiv_rn(wy, g.res_y)), (float)cy);
+    return true;
+}
+
+__device__ __forceinline__ int8_t clamp_add(int8_t v, int d)
+{
+    int t = (int)v + d;
+    return (int8_t)(t < -kClamp ? -kClamp : t > kClamp ? kClamp : t);
+}
+
+// free cells: block = one beam, threads stride over the Bresenham steps.  Step k of traceRay is
+// closed-form: x = sx+k, y = sy + ystep*m_k, m_k = max(0, ceil((k*deltay - deltax/2)/deltax)).
+// The first thread to set a cell's bit this frame applies the -1 (== the reference's bool mask).
+__global__ void __launch_bounds__(128)
+k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
+           const float *__restrict__ scan, const float *__restrict__ angle,
+           unsigned *__restrict__ free_bits, int *__restrict__ counters)
+{
+    const int j = blockIdx.x;
+    int cx, cy; center_cell(g, res->pose[0], res->pose[1], cx, cy);
+    float wx, wy;
+    int mine = 0;
+    if (beam_hit(g, res->pose, cx, cy, angle[j], scan[j], wx, wy)) {
+        int sx = cx, sy = cy, ex = (int)wx, ey = (int)wy;
+        const bool steep = abs(ey - sy) > abs(ex - sx);
+        int t;
+        if (steep) { t = sx; sx = sy; sy = t; t = ex; ex = ey; ey = t; }
+        if (sx > ex) { t = sx; sx = ex; ex = t; t = sy; sy = ey; ey = t; }
+        const int deltax = ex - sx, deltay = abs(ey - sy), e0 = deltax / 2;
+        const int ystep = ey > sy ? 1 : -1;
+        for (int k = threadIdx.x; k < deltax; k += blockDim.x) {
+            int num = k * deltay - e0;
+            int m = num > 0 ? (num + deltax - 1) / deltax : 0;
+            int xx = sx + k, yy = sy + ystep * m;
+            int idx = steep ? yy * g.w + xx : xx * g.w + yy;
+            if (xx < g.w && yy < g.h && xx >= 0 && yy >= 0 && idx < g.w * g.h) {
+                unsigned bit = 1u << (idx & 31);
+                unsigned old = atomicOr(&free_bits[idx >> 5], bit);
+                if (!(old & bit)) { grid[idx] = clamp_add(grid[idx], kFreeWeight); mine++; }
+            }
+        }
+    }
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (mine) atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(&counters[0], s_cnt);
+}
+
+// wall cells: one thread per beam; runs after k_map_free has completed (stream order), so the
+// +4 lands on top of the -1 exactly like the reference's two kernUpdateMap launches.
+__global__ void __launch_bounds__(128)
+k_map_wall(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
+           const float *__restrict__ scan, const float *__restrict__ angle, int n_beams,
+           unsigned *__restrict__ wall_bits, int *__restrict__ counters)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int mine = 0;
+    if (j < n_beams) {
+        int cx, cy; center_cell(g, res->pose[0], res->pose[1], cx, cy);
+        float wx, wy;
+        if (beam_hit(g, res->pose, cx, cy, angle[j], scan[j], wx, wy)) {
+            if (wx >= 0.0f && wx < (float)g.w && wy >= 0.0f && wy < (float)g.h) {
+                int idx = (int)__fmaf_rn(wx, (float)g.w, wy);
+                unsigned bit = 1u << (idx & 31);
+                unsigned old = atomicOr(&wall_bits[idx >> 5], bit);
+                if (!(old & bit)) { grid[idx] = clamp_add(grid[idx], kOccupiedWeight); mine = 1; }
+            }
+        }
+    }
+    int c = __syncthreads_count(mine);
+    if (threadIdx.x == 0 && c) atomicAdd(&counters[1], c);
+}
+
+__global__ void k_finish_counters(FrameResult *__restrict__ res, int *__restrict__ counters)
+{
+    res->n_free = counters[0]; res->n_wall = counters[1]; res->n_slow = counters[2];
+    counters[0] = 0; counters[1] = 0; counters[2] = 0;
+}
+
+}  // namespace pf

