@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- LiDAR frames/s of the particle-filter step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles P]
+
+A step = one LiDAR frame through the whole 2D particle-filter step (motion, scoring, extrema,
+weights, map update, resample) at 65 536 particles per GPU (BASELINE.json configs[1]).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BEAMS = 1081
+METRIC = "lidar_frames_per_sec_at_65536_particles_per_gpu"
+UNIT = "frames/s"
+
+
+def workload_scans(n_frames):
+    """real train_lidar0 scans (committed 256-frame fixture), played 1..255..1.. (ping-pong keeps the
+    motion physically continuous for any number of steps)"""
+    from gpu_icp_slam_b200 import scans as S
+    fx = S.load(os.path.join(ROOT, "tests", "golden", "train_lidar0_first256.scans.u16"))
+    order, f, d = [], 1, 1
+    for _ in range(n_frames):
+        order.append(f)
+        if f + d > 255 or f + d < 1:
+            d = -d
+        f += d
+    return np.ascontiguousarray(fx[order]), order
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.p = None
+        self.lines = []
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            t = [v.strip() for v in ln.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1])); mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_frames_per_sec(n_particles, n_frames, threads):
+    """The reference's CPU implementation of the path on the host cores: the reference's own
+    EvaluateParticle / ParticleAddNoise (oracle/_ref/libref.so, unmodified sources) when that
+    library was built, else the oracle port; particle ranges fanned over `threads` host threads
+    for the scoring (ctypes releases the GIL); the O(N) remainder (extrema, weights, map update,
+    resample) runs through the oracle port on one thread.  Returns (frames/s, kind, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from helpers import P
+    o = helpers.load_oracle()
+    ref = helpers.load_ref()
+    kind = "reference" if ref is not None else "port"
+    # reference-CPU flavour of the arithmetic: libm trig, separate multiply-add (host g++ build)
+    cfg = helpers.ocfg(helpers.TRIG_LIBM, helpers.MAD_SEPARATE)
+    of = helpers.OracleFilter(n_particles, cfg)
+    scans, order = workload_scans(n_frames + 2)
+    bounds = np.linspace(0, n_particles, threads + 1).astype(int)
+    fit = np.zeros(n_particles, np.int32)
+
+    def score_range(k, sc):
+        a, b = int(bounds[k]), int(bounds[k + 1])
+        if b <= a:
+            return
+        if ref is not None:
+            ref.ref_evaluate_particles(P(of.grid, helpers.bp), cfg.map_w, cfg.map_h, cfg.scale_x, cfg.scale_y,
+                                       cfg.res_x, cfg.res_y, P(of.x[a:b]), P(of.y[a:b]), P(of.th[a:b]), b - a,
+                                       P(sc), P(fit[a:b], helpers.ip))
+        else:
+            o.pfo_score2d_many(C.byref(cfg), P(of.grid, helpers.bp), P(of.x[a:b]), P(of.y[a:b]), P(of.th[a:b]),
+                               b - a, P(sc), P(fit[a:b], helpers.ip))
+
+    def frame(i):
+        sc = np.ascontiguousarray(scans[i])
+        f = order[i]
+        o.pfo_motion(of.s, f)
+        ths = [threading.Thread(target=score_range, args=(k, sc)) for k in range(threads)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        # the remainder of PFMeasurementUpdate / PFUpdateMap / PFResample through the port, fed the
+        # scores computed above
+        np.copyto(of.fit, fit)
+        s = of.s.contents
+        mn, mx, am = C.c_int32(), C.c_int32(), C.c_int()
+        o.pfo_minmax(of.s.contents.fit, n_particles, C.byref(mn), C.byref(mx), C.byref(am))
+        rng = mx.value - mn.value
+        if rng > 0:
+            w = of.weff
+            w *= (fit.astype(np.float32) - np.float32(mn.value)) * np.float32(1.0 / rng)
+        np.copyto(of.w, of.weff)
+        s.robot[0], s.robot[1], s.robot[2] = float(of.x[am.value]), float(of.y[am.value]), float(of.th[am.value])
+        o.pfo_update_map(of.s, P(sc))
+        o.pfo_resample(of.s, f)
+
+    frame(0)                                  # warm the map
+    t0 = time.perf_counter()
+    for i in range(1, n_frames + 1):
+        frame(i)
+    dt = time.perf_counter() - t0
+    of.close()
+    what = ("%d frames of the workload at %d particles; scoring = %s fanned over %d host threads, "
+            "O(N) remainder through the oracle port on 1 thread" %
+            (n_frames, n_particles, "reference EvaluateParticle (oracle/_ref)" if ref is not None else "oracle port", threads))
+    return n_frames / dt, kind, what
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.particles
+    # each "step" = one frame; bound the whole run to a couple of minutes
+    per_frame_guess = n * N_BEAMS * 35e-9 / max(1, threads * 0.8) + n * 1.2e-6
+    budget = 150.0
+    k = max(1, min(args.steps, int(budget / max(per_frame_guess, 1e-3))))
+    fps, kind, what = cpu_reference_frames_per_sec(n, k, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": k, "warmup": 1, "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "real train_lidar0 scans (committed 256-frame fixture, ping-pong)",
+        "config": {"workload": "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, %d particles, CPU" % n,
+                   "particles_per_gpu": n, "beams": N_BEAMS},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": kind, "sample": what},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import gpu_icp_slam_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.particles
+    K, W = args.steps, max(args.warmup, 3)
+    scans, order = workload_scans(K + W + 8)
+    stream = torch.cuda.current_stream()
+
+    if world > 1:
+        from gpu_icp_slam_b200.dist import ShardedParticleFilter
+        pf = ShardedParticleFilter(n, device=local_rank)
+    else:
+        pf = g.ParticleFilter(n, device=local_rank)
+        pf.set_stream(stream.cuda_stream)
+
+    scans_dev = torch.from_numpy(scans).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_async(i):
+        if world > 1:
+            pf.step_device(scans_dev[i].data_ptr(), order[i])
+        else:
+            pf.step_async(order[i], scans_dev[i].data_ptr())
+
+    # ---- warm-up (untimed): builds the map, first-launch costs
+    for i in range(W):
+        step_async(i)
+    sync_all()
+
+    # ---- `value`: K steps, inputs resident in HBM, device time per step by CUDA events on the launch
+    # stream, L2 flushed (256 MiB memset, untimed) between steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = pf.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        ev[k][0].record(stream)
+        step_async(W + k)
+        ev[k][1].record(stream)
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    launches = pf.launch_count - l0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # back-to-back (no flush) for reference: the streaming steady state
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(K):
+        step_async(W + k)
+    e1.record(stream)
+    sync_all()
+    b2b_ms = e0.elapsed_time(e1)
+
+    # ---- roofline of the dominant kernel (scoring), live CUDA events around that kernel alone
+    eng = pf.engine if world > 1 else pf
+    ker_ms, phase_ms = [], []
+    for k in range(min(K, 50)):
+        flush.fill_(k & 0xff)
+        a, b = eng.profile_score()
+        ker_ms.append(a); phase_ms.append(b)
+    ker = float(np.mean(ker_ms))
+    r = eng.fetch_result()
+
+    # ---- e2e: the public host API, host scan in, host pose out, every step
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(K):
+        if world > 1:
+            pf.step(scans[W + k], order[W + k])
+        else:
+            pf.step(scans[W + k], order[W + k])
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+
+    # max over ranks
+    t = torch.tensor([dev_ms, b2b_ms, e2e_s * 1e3, ker], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, b2b_ms, e2e_ms, ker = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        scale = world * n / 65536.0                      # 65 536-particle frame equivalents per frame
+        alg_bytes = n * (N_BEAMS + 20) + 4 * N_BEAMS     # N*1101 + 4324 per launch (per GPU)
+        achieved = alg_bytes / (ker * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": K / (dev_ms * 1e-3) * scale, "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "real train_lidar0 scans (committed 256-frame fixture, ping-pong); the full .mat is not on the GPU box",
+            "config": {"workload": "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, 65 536 particles per GPU",
+                       "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS,
+                       "score_mode": "filtered (bit-exact)", "l2_flush": "256 MiB memset between timed steps (untimed)",
+                       "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
+                       "parallelism": "particles sharded %d-way, map replicated" % world},
+            "value_back_to_back": K / (b2b_ms * 1e-3) * scale,
+            "wall_s_timed_region": t_wall,
+            "e2e": {"value": K / (e2e_ms * 1e-3) * scale, "unit": UNIT,
+                    "h2d_bytes_per_step": 4 * N_BEAMS, "d2h_bytes_per_step": C.sizeof(g.FrameResult)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_score_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker,
+                         "scoring_phase_ms": float(np.mean(phase_ms))},
+            "clocks": clocks,
+            "last_frame": {"neff": r.neff, "resampled": r.resampled, "n_slow_evals": r.n_slow_evals,
+                           "slow_eval_frac": r.n_slow_evals / float(n * N_BEAMS)},
+        }
+        if not args.no_cpu and world == 1:
+            fps, kind, what = cpu_reference_frames_per_sec(n, max(2, min(8, int(20.0 / (n * N_BEAMS * 35e-9 + 1e-3)))), 1)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": kind, "sample": what}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=65536, help="particles per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -240,12 +240,15 @@ static int score_filtered_launch(const int8_t *grid, MapGeom g, const float *x, 
                                  const float *th, int n, int gidx0, const float *scan,
                                  const float *angle, int n_beams, int *fit, int *blk_min,
                                  long long *blk_maxkey, Extrema *ext_local, ScoreFilteredWork *wk,
-                                 int *partial, int *counters, cudaStream_t stream)
+                                 int *partial, int *counters, cudaStream_t stream,
+                                 cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
     k_beam_prep<<<1, 1024, 0, stream>>>(scan, angle, n_beams, g, wk);
     dim3 grid_fast((n + kFastThreads - 1) / kFastThreads, kFastSlices);
+    if (ev0) cudaEventRecord(ev0, stream);
     k_score_fast<<<grid_fast, kFastThreads, 0, stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
                                                          partial, counters);
+    if (ev1) cudaEventRecord(ev1, stream);
     k_score_slow<<<(n + 255) / 256, 256, 0, stream>>>(grid, g, x, y, th, n, scan, angle, wk,
                                                       partial + (size_t)kFastSlices * n);
     const int nblk = (n + kTile - 1) / kTile;

@@ -259,14 +259,16 @@ int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
     return PFSLAM_OK;
 }
 
-int pfslam_phase_score(pfslam_engine *e, const float *scan_dev)
+static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     const float *scan = scan_dev ? scan_dev : e->scan;
     if (e->cfg.score_mode == PFSLAM_SCORE_EXACT) {
+        if (ev0) cudaEventRecord(ev0, e->stream);
         k_score_exact<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(
             e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle, e->cfg.n_beams,
             e->fit, e->blk_min, e->blk_maxkey);
+        if (ev1) cudaEventRecord(ev1, e->stream);
         e->launches++;
         CUDA_TRY(cudaGetLastError());
         k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y,
@@ -275,13 +277,34 @@ int pfslam_phase_score(pfslam_engine *e, const float *scan_dev)
     } else {
         int nl = score_filtered_launch(e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                        e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local,
-                                       e->fwork, e->score_partial, e->counters, e->stream);
+                                       e->fwork, e->score_partial, e->counters, e->stream, ev0, ev1);
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "filtered scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
         e->launches += nl;
     }
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
+}
+
+int pfslam_phase_score(pfslam_engine *e, const float *scan_dev) { return score_phase(e, scan_dev, nullptr, nullptr); }
+
+int pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase)
+{
+    if (!e || !ms_kernel || !ms_phase) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+    CUDA_TRY(cudaEventRecord(ev[0], e->stream));
+    int rc = score_phase(e, nullptr, ev[1], ev[2]);
+    if (rc == PFSLAM_OK) {
+        cudaEventRecord(ev[3], e->stream);
+        cudaError_t ce = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(ms_kernel, ev[1], ev[2]);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(ms_phase, ev[0], ev[3]);
+        if (ce != cudaSuccess) rc = set_error(PFSLAM_ERR_CUDA, "profile_score: %s", cudaGetErrorString(ce));
+    }
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+    return rc;
 }
 
 int pfslam_phase_weights(pfslam_engine *e)

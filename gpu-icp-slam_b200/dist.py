@@ -1,0 +1,96 @@
+"""Multi-GPU particle filter: particles sharded N/R per GPU, map replicated.
+
+One process per GPU (torchrun); `torch.distributed` is the plumbing.  Per frame the shards exchange
+  1. the post-noise poses (all-gather, 12 B/particle) -- the resampler's pre-resample snapshot,
+  2. per-rank score extrema {min, max, first arg-max, its pose} (all-gather, 32 B/rank),
+  3. per-tile weight sums + tile-local CDF values (all-gather, ~4 B/particle),
+and every rank then derives the identical global min/max/robotPos, Neff, resample decision, CDF
+and map update.  Random streams are seeded by GLOBAL particle index and every floating-point
+reduction has a fixed global tile order, so the trajectory is bit-identical for any rank count.
+
+`ShardedParticleFilter` drives any engine that implements the phase protocol of
+`engine.ParticleFilter` (the CUDA engine on GPUs; tests drive it with a CPU stand-in over gloo).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import engine as _engine
+
+
+class _CudaArray:
+    """minimal __cuda_array_interface__ holder so torch can alias an engine-owned device buffer"""
+
+    def __init__(self, ptr, nbytes, typestr, itemsize):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes // itemsize,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def cuda_exchange_tensors(pf, device):
+    """torch tensors aliasing the engine's exchange buffers (include/pfslam.h PFSLAM_BUF_*)."""
+    import torch
+    out = {}
+    for name, which, typestr in (("ext_local", _engine.BUF_EXTREMA_LOCAL, "<i4"), ("ext_all", _engine.BUF_EXTREMA_ALL, "<i4"),
+                                 ("tiles_local", _engine.BUF_TILES_LOCAL, "<f4"), ("tiles_all", _engine.BUF_TILES_ALL, "<f4"),
+                                 ("pose_local", _engine.BUF_POSE_LOCAL, "<f4"), ("pose_all", _engine.BUF_POSE_ALL, "<f4")):
+        ptr, nbytes = pf.device_buffer(which)
+        out[name] = torch.as_tensor(_CudaArray(ptr, nbytes, typestr, 4), device=torch.device("cuda", device))
+    return out
+
+
+def _all_gather(dist, out, inp, group):
+    try:
+        dist.all_gather_into_tensor(out, inp, group=group)
+    except (RuntimeError, NotImplementedError):
+        chunks = list(out.view(dist.get_world_size(group), -1).unbind(0))
+        dist.all_gather(chunks, inp.view(-1), group=group)
+
+
+class ShardedParticleFilter:
+    """The whole filter = world_size shards of `n_per_rank` particles, one per process."""
+
+    def __init__(self, n_per_rank, device=0, group=None, engine_factory=None, **engine_kw):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n = int(n_per_rank)
+        self.n_global = self.n * self.world
+        if self.world > 1 and self.n % 1024 != 0:
+            raise _engine.PfslamError("sharded filters need n_per_rank % 1024 == 0 (tile-aligned shards)")
+        kw = dict(n_particles_global=self.n_global, particle_offset=self.rank * self.n, n_ranks=self.world)
+        kw.update(engine_kw)
+        if engine_factory is None:
+            import torch
+            self.engine = _engine.ParticleFilter(self.n, device=device, **kw)
+            self.engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            self.t = cuda_exchange_tensors(self.engine, device)
+        else:
+            self.engine = engine_factory(self.n, **kw)
+            self.t = self.engine.exchange_tensors()
+
+    # -- one frame; nothing here synchronises the host ---------------------------------------------
+    def step_device(self, scan_dev_ptr, frame):
+        e, t, d, g = self.engine, self.t, self.dist, self.group
+        e.phase_motion(frame)
+        _all_gather(d, t["pose_all"], t["pose_local"], g)       # pre-resample snapshot of every shard
+        e.phase_score(scan_dev_ptr)
+        _all_gather(d, t["ext_all"], t["ext_local"], g)         # min / max / first arg-max / best pose
+        e.phase_weights()
+        _all_gather(d, t["tiles_all"], t["tiles_local"], g)     # tile sums of w, w^2 and the tile-local CDF
+        e.phase_map(scan_dev_ptr)                                # prefix + Neff + robotPos, then the map update
+        e.phase_resample(frame)
+
+    def step(self, scan_host, frame):
+        """particleFilter(pbo, frame, lidar) for the sharded filter: host scan in, result out."""
+        self.engine.upload_scan(scan_host)
+        self.step_device(None, frame)
+        return self.engine.fetch_result()
+
+    @property
+    def launch_count(self):
+        return self.engine.launch_count
+
+    def close(self):
+        self.engine.close()

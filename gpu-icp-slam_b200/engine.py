@@ -89,6 +89,7 @@ _SIGS = {
     "pfslam_synchronize": (C.c_int, [C.c_void_p]),
     "pfslam_device_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pfslam_launch_count": (C.c_int64, [C.c_void_p]),
+    "pfslam_profile_score": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pfslam_debug_trig": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
@@ -283,6 +284,12 @@ class ParticleFilter:
         fit = np.empty(self.n, dtype=np.int32)
         self._check(self._lib.pfslam_score_particles(self._h, s.ctypes.data, fit.ctypes.data))
         return fit
+
+    def profile_score(self):
+        """(ms of the dominant scoring kernel alone, ms of the whole scoring phase), CUDA events."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self._lib.pfslam_profile_score(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def update_grid(self, scan, pose):
         """PFUpdateMap alone (src/kernel.cu:551) for an explicit robot pose."""

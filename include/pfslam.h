@@ -129,6 +129,11 @@ int  pfslam_device_buffer(pfslam_engine *e, int32_t which, void **dev_ptr, int64
 /* number of kernels this engine has launched (bench.py's gpu_launches) */
 int64_t pfslam_launch_count(pfslam_engine *e);
 
+/* measurement hook for bench.py's roofline: runs the scoring phase once on the engine stream with
+ * CUDA events around the dominant kernel alone (k_score_fast or k_score_exact) and around the whole
+ * phase; returns both durations in milliseconds after synchronising */
+int  pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase);
+
 /* test hook: libdevice cosf/sinf of n host floats evaluated on the device (the functions the
  * reference's kernels call, kernel.cu:185-186); used to validate the oracle's emulation */
 int  pfslam_debug_trig(int32_t device, const float *x_host, int64_t n, float *cos_out, float *sin_out);

@@ -84,6 +84,7 @@ def load_oracle():
     o.pfo_apply_masks.argtypes = [bp, C.c_int, ubp, ubp]
     o.pfo_scan.restype = C.c_float
     o.pfo_scan.argtypes = [fp, C.c_int, fp]
+    o.pfo_scan_tiles.argtypes = [fp, C.c_int, fp, fp]
     o.pfo_resample_src.restype = C.c_int
     o.pfo_resample_src.argtypes = [fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
     o.pfo_create.restype = C.POINTER(OState)
