@@ -1,0 +1,567 @@
+// pf_score_tiled.cuh -- scoring v3: TMA-staged occupancy-grid tiles in shared memory.
+//
+// Same contract as pf_score_filtered.cuh (bit-identical to the reference's kernEvaluateParticles,
+// src/kernel.cu:257-284), restructured for the B200 memory system:
+//
+//   * the dense list of fast beams is cut into chunks of 32 consecutive beams; consecutive beams
+//     hit a contiguous wall segment, so the hit cells of a chunk -- for EVERY particle of the cloud
+//     (conservative interval bound from the cloud's pose bounds) -- fit a 128x128-cell window.
+//     That window is staged into shared memory by one TMA 2D box load per (block, chunk),
+//     double-buffered behind an mbarrier; out-of-map parts are zero-filled by the TMA unit, which
+//     IS the reference's bounds test (out-of-map cells contribute 0, kernel.cu:248);
+//   * 2^-16-cell fixed point relative to the window origin inside the float mantissa (magic 2^23):
+//     two packed FFMA2 give both axes; the cell byte of each axis is byte 2 of the result, so ONE
+//     PRMT builds the shared-memory offset (x*256 + y) and one LDS.S8 fetches the cell;
+//   * the rounding guard band (+-128 units = +-1.95e-3 cell, error bound 44 units) is
+//     "byte 1 == 0"; uncertain pairs set a bit in a per-particle 32-bit mask (one bit per beam of
+//     the chunk), are compacted into a shared-memory queue after the chunk and re-evaluated with
+//     the reference's exact expression;
+//   * beams whose conservative box does not fit the chunk window (depth discontinuities, wide
+//     clouds) go to the v2 LDG kernel (k_score_fast), out-of-domain beams to k_score_slow.
+#pragma once
+#include <cuda.h>
+
+#include "pf_score_filtered.cuh"
+
+namespace pf {
+
+constexpr int kTileX = 128;                 // window rows (x cells) and usable columns (y cells)
+constexpr int kTileBytes = kTileX * kTileX; // dense TMA box: 128 (y, contiguous) x 128 (x) bytes
+constexpr int kSkewPitch = 260;             // bank-conflict-free row pitch of the gather copy
+constexpr int kSkewBytes = kTileX * kSkewPitch + 16;
+constexpr int kChunkBeams = 32;
+constexpr int kMaxGroups = 64;              // groups of 32 consecutive fast beams (2048 beams)
+constexpr int kMaxChunks = 2 * kMaxGroups;  // each group gets up to two windows
+constexpr int kTiledThreads = 256;
+constexpr int kTiledPPT = 4;                // particles per thread
+constexpr int kTiledGroup = kTiledThreads * kTiledPPT;
+constexpr int kTiledY = 6;                  // chunk-interleaved blocks per particle group (grid.y)
+constexpr int kTiledQueueCap = 2048;
+constexpr float kMagicT = 8388608.0f;       // 2^23
+constexpr int kFracT = 16;
+constexpr float kGuardT = 128.0f;           // units of 2^-16 cell
+constexpr int kBoxMargin = 2;               // cells added around the conservative hit box
+
+struct TileChunk { int x0, y0, count, pad; };
+
+struct TiledWork {
+    int n_chunks, pad0, pad1, pad2;
+    TileChunk chunk[kMaxChunks];
+    int order[kMaxChunks];                     // non-empty window slots, in beam order
+    float4 tconst[kMaxChunks * kChunkBeams];   // {-Bx, Ay, Ax, By} in 2^-16-cell units (two FFMA2 operand pairs)
+    int tbeam[kMaxChunks * kChunkBeams];       // original beam index
+    int bounds[8];                             // cloud bounds as ordered ints: xmin,xmax,ymin,ymax,tmin,tmax
+};
+
+__device__ __forceinline__ int float_order(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float order_float(int k)
+{
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+__global__ void k_bounds_reset(TiledWork *__restrict__ tw)
+{
+    if (threadIdx.x < 3) { tw->bounds[2 * threadIdx.x] = 0x7fffffff; tw->bounds[2 * threadIdx.x + 1] = (int)0x80000000; }
+}
+
+// pose bounds of the local particle cloud (min/max of x, y, theta)
+__global__ void __launch_bounds__(256)
+k_cloud_bounds(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
+               TiledWork *__restrict__ tw)
+{
+    __shared__ int s_b[6];
+    if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
+    __syncthreads();
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int k0 = float_order(x[i]), k1 = float_order(y[i]), k2 = float_order(th[i]);
+        lo[0] = min(lo[0], k0); hi[0] = max(hi[0], k0);
+        lo[1] = min(lo[1], k1); hi[1] = max(hi[1], k1);
+        lo[2] = min(lo[2], k2); hi[2] = max(hi[2], k2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_b[2 * c], lo[c]); atomicMax(&s_b[2 * c + 1], hi[c]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        if (threadIdx.x & 1) atomicMax(&tw->bounds[threadIdx.x], s_b[threadIdx.x]);
+        else atomicMin(&tw->bounds[threadIdx.x], s_b[threadIdx.x]);
+    }
+}
+
+// range of cos / sin over the angle interval [p0, p1]
+__device__ __forceinline__ void trig_range(double p0, double p1, double &cmin, double &cmax, double &smin, double &smax)
+{
+    const double PI = 3.14159265358979323846;
+    double c0 = cos(p0), c1 = cos(p1), s0 = sin(p0), s1 = sin(p1);
+    cmin = fmin(c0, c1); cmax = fmax(c0, c1); smin = fmin(s0, s1); smax = fmax(s0, s1);
+    if (!(p1 - p0 < 6.0)) { cmin = smin = -1.0; cmax = smax = 1.0; return; }
+    // extrema: cos = +1 at 2k*pi, -1 at (2k+1)*pi; sin = +1 at pi/2 + 2k*pi, -1 at -pi/2 + 2k*pi
+    if (floor(p1 / (2 * PI)) > floor(p0 / (2 * PI)) || p0 == 0.0) cmax = 1.0;
+    if (floor((p1 - PI) / (2 * PI)) > floor((p0 - PI) / (2 * PI))) cmin = -1.0;
+    if (floor((p1 - PI / 2) / (2 * PI)) > floor((p0 - PI / 2) / (2 * PI))) smax = 1.0;
+    if (floor((p1 + PI / 2) / (2 * PI)) > floor((p0 + PI / 2) / (2 * PI))) smin = -1.0;
+}
+
+// Per-frame preparation (one block, 1024 threads, up to 2048 beams): classify every beam as
+//   slow  (outside the fast domain: r >= 20 m, sentinel, NaN)        -> wk->slow   (k_score_slow)
+//   tiled (conservative hit box fits its chunk's 128x128 window)    -> tw chunks  (k_score_tiled)
+//   wide  (fast domain, but does not fit)                           -> wk->fconst (k_score_fast)
+__global__ void __launch_bounds__(1024)
+k_tile_prep(const float *__restrict__ scan, const float *__restrict__ angle, int n_beams, MapGeom g,
+            ScoreFilteredWork *__restrict__ wk, TiledWork *__restrict__ tw)
+{
+    __shared__ int s_scan[32];
+    __shared__ int4 s_box[2048];
+    __shared__ int s_j[2048];
+    __shared__ int s_nelig, s_nslow, s_nwide;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) { s_nwide = 0; }
+    const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
+    const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
+    const double pxmin = (double)order_float(tw->bounds[0]), pxmax = (double)order_float(tw->bounds[1]);
+    const double pymin = (double)order_float(tw->bounds[2]), pymax = (double)order_float(tw->bounds[3]);
+    const double tmin = (double)order_float(tw->bounds[4]), tmax = (double)order_float(tw->bounds[5]);
+    // the fixed-point error bound assumes poses within kFastMaxPoseCells of the map centre
+    const double lim_x = (double)kFastMaxPoseCells * (double)g.res_x, lim_y = (double)kFastMaxPoseCells * (double)g.res_y;
+    const bool cloud_ok = pxmin <= pxmax && pymin <= pymax && tmin <= tmax &&
+                          fabs(pxmin) < lim_x && fabs(pxmax) < lim_x && fabs(pymin) < lim_y && fabs(pymax) < lim_y &&
+                          fabs(tmin) < 1e3 && fabs(tmax) < 1e3;
+
+    // ---- phase A: thread t owns beams 2t, 2t+1
+    bool elig[2], slow[2];
+    int4 box[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int j = 2 * t + k;
+        elig[k] = slow[k] = false;
+        box[k] = make_int4(0, 0, 0, 0);
+        if (j < n_beams) {
+            const float r = scan[j];
+            const double rx = (double)r / (double)g.res_x, ry = (double)r / (double)g.res_y;
+            const bool fast = fabs(rx) < (double)kFastMaxCells && fabs(ry) < (double)kFastMaxCells;
+            slow[k] = !fast;
+            if (fast) {
+                elig[k] = true;
+                if (cloud_ok) {
+                    double cmin, cmax, smin, smax;
+                    const double a = (double)angle[j];
+                    trig_range(a + tmin - 1e-6, a + tmax + 1e-6, cmin, cmax, smin, smax);
+                    const double xa = rx * cmin, xb = rx * cmax, ya = ry * smin, yb = ry * smax;
+                    const double vx0 = (double)c0x + pxmin / (double)g.res_x + fmin(xa, xb);
+                    const double vx1 = (double)c0x + pxmax / (double)g.res_x + fmax(xa, xb);
+                    const double vy0 = (double)c0y + pymin / (double)g.res_y + fmin(ya, yb);
+                    const double vy1 = (double)c0y + pymax / (double)g.res_y + fmax(ya, yb);
+                    box[k] = make_int4((int)floor(vx0) - kBoxMargin, (int)ceil(vx1) + kBoxMargin,
+                                       (int)floor(vy0) - kBoxMargin, (int)ceil(vy1) + kBoxMargin);
+                } else {
+                    box[k] = make_int4(-(1 << 20), 1 << 20, -(1 << 20), 1 << 20);   // never fits -> wide
+                }
+            }
+        }
+    }
+    // dense indices (beam order) by a block scan of per-thread counts
+    const int ce = (int)elig[0] + (int)elig[1], cs = (int)slow[0] + (int)slow[1];
+    int v = ce | (cs << 16);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    if (lane == 31) s_scan[warp] = v;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < 32; w++) { if (w < warp) base += s_scan[w]; tot += s_scan[w]; }
+    const int excl = base + v - (ce | (cs << 16));
+    int de = excl & 0xffff, ds = excl >> 16;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (elig[k]) { s_box[de] = box[k]; s_j[de] = 2 * t + k; de++; }
+        if (slow[k]) { wk->slow[ds] = 2 * t + k; ds++; }
+    }
+    if (t == 0) { s_nelig = tot & 0xffff; s_nslow = tot >> 16; }
+    __syncthreads();
+    const int nelig = s_nelig;
+
+    // ---- phase B: warp w owns beam group w (and w+32).  A group gets a window placed on all of its
+    // beams; the beams that do not fit get a second window of their own; what still does not fit is
+    // "wide" and goes to the LDG kernel.
+    const int n_groups = (nelig + kChunkBeams - 1) / kChunkBeams;
+    for (int c = warp; c < n_groups; c += 32) {
+        const int d = c * kChunkBeams + lane;
+        const bool have = d < nelig;
+        const int4 b = have ? s_box[d] : make_int4(0, 0, 0, 0);
+        bool todo = have;
+        double rx = 0, ry = 0, ca = 0, sa = 0;
+        int j = 0;
+        if (have) {
+            j = s_j[d];
+            const double r = (double)scan[j], a = (double)angle[j];
+            rx = r / (double)g.res_x; ry = r / (double)g.res_y; ca = cos(a); sa = sin(a);
+        }
+        if (lane == 0) { tw->chunk[2 * c].count = 0; tw->chunk[2 * c + 1].count = 0; }
+        __syncwarp();
+        for (int pass = 0; pass < 2; pass++) {
+            int x0 = todo ? b.x : 0x3fffffff, x1 = todo ? b.y : -0x3fffffff;
+            int y0 = todo ? b.z : 0x3fffffff, y1 = todo ? b.w : -0x3fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+                y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+            }
+            const unsigned tm = __ballot_sync(0xffffffffu, todo);
+            if (!tm) break;
+            // fallback anchor when the span is too large: the middle beam still to place
+            const int mid_lane = __fns(tm, 0, (__popc(tm) + 1) / 2);
+            const int mx = (__shfl_sync(0xffffffffu, b.x, mid_lane) + __shfl_sync(0xffffffffu, b.y, mid_lane)) / 2;
+            const int my = (__shfl_sync(0xffffffffu, b.z, mid_lane) + __shfl_sync(0xffffffffu, b.w, mid_lane)) / 2;
+            int ox, oy;
+            if ((long long)x1 - x0 < kTileX - 1) ox = x0 - (kTileX - 1 - (x1 - x0)) / 2;
+            else ox = mx - kTileX / 2;
+            // y is the contiguous dimension of the grid: the TMA box must start on a 16-byte boundary
+            // there (measured on B200: unaligned inner coordinates fault), so the y origin is aligned down
+            if ((long long)y1 - y0 < kTileX - 1) { const int slack = kTileX - 2 - (y1 - y0); oy = y0 - 1 - max(0, slack - 15) / 2; }
+            else oy = my - kTileX / 2;
+            ox = max(-100000, min(100000, ox));
+            oy = (max(-100000, min(100000, oy)) >> 4) << 4;
+            const bool member = todo && b.x >= ox + 1 && b.y <= ox + kTileX - 2 && b.z >= oy + 1 && b.w <= oy + kTileX - 2;
+            const unsigned mm = __ballot_sync(0xffffffffu, member);
+            const int slot = 2 * c + pass;
+            if (member) {
+                const double u = (double)(1 << kFracT);
+                const int k = __popc(mm & ((1u << lane) - 1));
+                tw->tconst[slot * kChunkBeams + k] = make_float4((float)(-rx * sa * u), (float)(ry * ca * u),
+                                                                 (float)(rx * ca * u), (float)(ry * sa * u));
+                tw->tbeam[slot * kChunkBeams + k] = j;
+                todo = false;
+            }
+            if (lane == 0) { TileChunk tc; tc.x0 = ox; tc.y0 = oy; tc.count = __popc(mm); tc.pad = 0; tw->chunk[slot] = tc; }
+        }
+        const unsigned wm = __ballot_sync(0xffffffffu, todo);
+        if (wm) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_nwide, __popc(wm));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (todo) {
+                const double u = (double)(1 << kFracBits);
+                const int k = wbase + __popc(wm & ((1u << lane) - 1));
+                wk->fconst[k] = make_float4((float)(rx * ca * u), (float)(-rx * sa * u), (float)(ry * ca * u), (float)(ry * sa * u));
+                wk->fbeam[k] = j;
+            }
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        // the score kernel walks the non-empty windows only
+        int m = 0;
+        for (int sl = 0; sl < 2 * n_groups; sl++)
+            if (tw->chunk[sl].count > 0) tw->order[m++] = sl;
+        tw->n_chunks = m; wk->nf = s_nwide; wk->ns = s_nslow;
+    }
+}
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// Shared-memory gather layout.  The PRMT offset is idx = x*256 + y; a row pitch of 256 B would put
+// every row in the same banks (measured: ~7 wavefronts per LDS).  One LEA.HI turns it into
+//     addr = idx + (idx >> 6) = x*260 + y + (y >> 6)
+// i.e. pitch 260 (bank = x + y/4 mod 32: a compact 2-D footprint is conflict free) with columns
+// 64..127 displaced by one byte.  The TMA box lands densely in `stage`; the block re-lays it out
+// into `skew` once per chunk (~40 instructions per thread against ~1200 in the beam loop).
+struct TiledSmem {
+    alignas(128) int8_t stage[kTileBytes];
+    alignas(16) int8_t skew[kSkewBytes];
+    alignas(16) float4 cst[2][kChunkBeams];
+    int beam[2][kChunkBeams];
+    unsigned queue[kTiledQueueCap];
+    int acc[kTiledGroup];
+    alignas(8) uint64_t bar;
+    int qn;
+};
+
+// Tiled scoring: block = 256 threads x 4 particles = 1024 particles; blockIdx.y interleaves the
+// frame's chunks.  partial row blockIdx.y gets this block's per-particle sums.
+__global__ void __launch_bounds__(kTiledThreads)
+k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
+              const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
+              const float *__restrict__ scan, const float *__restrict__ angle,
+              const TiledWork *__restrict__ tw, int *__restrict__ partial, int *__restrict__ counters)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int p0 = blockIdx.x * kTiledGroup + tid;
+    const int n_chunks = tw->n_chunks;
+    const int c_first = blockIdx.y;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.qn = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kTiledPPT; k++) sm.acc[tid + k * kTiledThreads] = 0;
+    __syncthreads();
+    // prologue: the first window of this block in flight
+    if (tid == 0 && c_first < n_chunks) {
+        mbar_expect_tx(&sm.bar, kTileBytes);
+        const int sl = tw->order[c_first];
+        tma_load_2d(sm.stage, &tmap, tw->chunk[sl].y0, tw->chunk[sl].x0, &sm.bar);
+    }
+
+    const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
+    const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
+    const float unit = (float)(1 << kFracT);
+    const float irx = (float)(1.0 / (double)g.res_x), iry = (float)(1.0 / (double)g.res_y);
+    const float mconst = kMagicT + 0.5f * unit + kGuardT;      // exact
+    float px[kTiledPPT], py[kTiledPPT];
+    float2 cc[kTiledPPT], ss[kTiledPPT];
+    int acc[kTiledPPT];
+#pragma unroll
+    for (int k = 0; k < kTiledPPT; k++) {
+        // lanes past the end take a copy of the last particle (results discarded), so every
+        // evaluation stays inside the staged window
+        const int p = min(p0 + k * kTiledThreads, n - 1);
+        px[k] = x[p]; py[k] = y[p];
+        const float a = th[p];
+        float sn, cs;
+        sincosf(a, &sn, &cs);
+        cc[k] = make_float2(cs, cs); ss[k] = make_float2(sn, sn);
+        acc[k] = 0;
+    }
+
+    int it = 0;
+    for (int ci = c_first; ci < n_chunks; ci += kTiledY, it++) {
+        const int s = it & 1;
+        const int c = tw->order[ci];
+        const TileChunk tc = tw->chunk[c];
+        if (tid < kChunkBeams) {
+            sm.cst[s][tid] = tid < tc.count ? tw->tconst[c * kChunkBeams + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+            sm.beam[s][tid] = tw->tbeam[c * kChunkBeams + tid];
+        }
+        // window-relative fixed-point offsets of this thread's particles
+        float2 P[kTiledPPT];
+        const float offx = __fsub_rn(c0x, (float)tc.x0), offy = __fsub_rn(c0y, (float)tc.y0);
+#pragma unroll
+        for (int k = 0; k < kTiledPPT; k++)
+            P[k] = make_float2(__fmaf_rn(__fmaf_rn(px[k], irx, offx), unit, mconst),
+                               __fmaf_rn(__fmaf_rn(py[k], iry, offy), unit, mconst));
+        mbar_wait(&sm.bar, it & 1);            // window landed in `stage`
+        {   // re-lay the dense 128x128 box out with pitch 260 (+1 for columns >= 64)
+            const int r = tid >> 1, h = tid & 1;
+            const uint4 *src = reinterpret_cast<const uint4 *>(sm.stage + r * kTileX + h * 64);
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const uint4 v = src[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sm.skew + r * kSkewPitch + h * 64);
+            if (h == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) dst[i] = w[i];
+            } else {
+                dst[0] = w[0] << 8;
+#pragma unroll
+                for (int i = 1; i < 16; i++) dst[i] = __funnelshift_l(w[i - 1], w[i], 8);
+                dst[16] = w[15] >> 24;
+            }
+        }
+        __syncthreads();                       // skewed window + constants visible; `stage` is free again
+        if (tid == 0) {
+            if (ci + kTiledY < n_chunks) {     // next window streams in while this one is scored
+                const int cn = tw->order[ci + kTiledY];
+                mbar_expect_tx(&sm.bar, kTileBytes);
+                tma_load_2d(sm.stage, &tmap, tw->chunk[cn].y0, tw->chunk[cn].x0, &sm.bar);
+            }
+        }
+        const int8_t *tile = sm.skew;
+        unsigned um[kTiledPPT];
+#pragma unroll
+        for (int k = 0; k < kTiledPPT; k++) um[k] = 0u;
+        const int cnt = tc.count;
+        unsigned bit = 1u;
+        // Main loop, ~10 instructions per evaluation: 2 FFMA2, PRMT, LEA.HI, LDS.S8, 4 for the guard-band
+        // test, then either the add (certain) or the beam's bit in the particle's mask (uncertain).
+#pragma unroll 4
+        for (int b = 0; b < cnt; b++) {
+            const float4 q = sm.cst[s][b];
+            const float2 lo = make_float2(q.x, q.y), hi = make_float2(q.z, q.w);
+#pragma unroll
+            for (int k = 0; k < kTiledPPT; k++) {
+                const float2 t2 = __ffma2_rn(hi, cc[k], __ffma2_rn(lo, ss[k], P[k]));
+                const uint32_t bx = __float_as_uint(t2.x), by = __float_as_uint(t2.y);
+                const uint32_t idx = prmt(bx, by, 0xBB26u);
+                const int v = (int)tile[idx + (idx >> 6)];
+                asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                    "and.b32 t, %2, 0xff00;\n\t"
+                    "setp.eq.u32 p, t, 0;\n\t"
+                    "and.b32 t, %3, 0xff00;\n\t"
+                    "setp.eq.or.u32 p, t, 0, p;\n\t"
+                    "@p or.b32 %0, %0, %4;\n\t"
+                    "@!p add.s32 %1, %1, %5;\n\t}"
+                    : "+r"(um[k]), "+r"(acc[k]) : "r"(bx), "r"(by), "r"(bit), "r"(v));
+            }
+            bit <<= 1;
+        }
+        // uncertain pairs (not added above): queue them for exact evaluation
+#pragma unroll
+        for (int k = 0; k < kTiledPPT; k++) {
+            unsigned m = (p0 + k * kTiledThreads < n) ? um[k] : 0u;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int qi = atomicAdd(&sm.qn, 1);
+                if (qi < kTiledQueueCap) sm.queue[qi] = ((unsigned)(tid + k * kTiledThreads) << 8) | (unsigned)b;
+                else {
+                    const int j = sm.beam[s][b];
+                    acc[k] += eval_exact(grid, g, c0x, c0y, px[k], py[k], th[p0 + k * kTiledThreads], angle[j], scan[j]);
+                }
+            }
+        }
+        __syncthreads();                       // all reads of the window done; queue complete
+        const int qn = min(sm.qn, kTiledQueueCap);
+        for (int qi = tid; qi < qn; qi += kTiledThreads) {
+            const unsigned e = sm.queue[qi];
+            const int pl = (int)(e >> 8), b = (int)(e & 0xffu);
+            const int p = blockIdx.x * kTiledGroup + pl;
+            const int j = sm.beam[s][b];
+            const int v = eval_exact(grid, g, c0x, c0y, x[p], y[p], th[p], angle[j], scan[j]);
+            if (v) atomicAdd(&sm.acc[pl], v);
+        }
+        __syncthreads();
+        if (tid == 0) { if (sm.qn) atomicAdd(&counters[2], sm.qn); sm.qn = 0; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTiledPPT; k++) {
+        const int p = p0 + k * kTiledThreads;
+        if (p < n) partial[(size_t)blockIdx.y * n + p] = acc[k] + sm.acc[tid + k * kTiledThreads];
+    }
+}
+
+// fit[p] = sum of n_rows partial rows; per-1024-particle min / max-key partials
+__global__ void __launch_bounds__(256)
+k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gidx0, int *__restrict__ fit,
+                     int *__restrict__ blk_min, long long *__restrict__ blk_maxkey)
+{
+    __shared__ int smin[8];
+    __shared__ long long smax[8];
+    int mn = 0x7fffffff;
+    long long mk = (long long)0x8000000000000000ull;
+    for (int k = 0; k < 4; k++) {
+        const int p = blockIdx.x * kTile + k * 256 + threadIdx.x;
+        if (p < n) {
+            int s = 0;
+            for (int r = 0; r < n_rows; r++) s += partial[(size_t)r * n + p];
+            fit[p] = s;
+            mn = min(mn, s);
+            long long t = extrema_key(s, gidx0 + p);
+            mk = t > mk ? t : mk;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        long long t = __shfl_xor_sync(0xffffffffu, mk, o);
+        mk = t > mk ? t : mk;
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { mn = min(mn, smin[w]); mk = smax[w] > mk ? smax[w] : mk; }
+        blk_min[blockIdx.x] = mn; blk_maxkey[blockIdx.x] = mk;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor map of the occupancy grid: uint8 [map_w rows (x)][map_h cols (y)], box 128 (y) x 128 (x)
+static int make_grid_tensor_map(CUtensorMap *out, const int8_t *grid, int map_w, int map_h)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+    if (map_h % 16 != 0) return -2;                       // TMA global stride must be a multiple of 16 B
+    cuuint64_t dims[2] = {(cuuint64_t)map_h, (cuuint64_t)map_w};
+    cuuint64_t strides[1] = {(cuuint64_t)map_h};
+    cuuint32_t box[2] = {(cuuint32_t)kTileX, (cuuint32_t)kTileX};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((PFN_encodeTiled)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)grid, dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+inline int score_tiled_rows() { return kTiledY + kFastSlices + 1; }
+
+static int score_tiled_setup()
+{
+    return cudaFuncSetAttribute(k_score_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem)) == cudaSuccess ? 0 : -1;
+}
+
+// returns the number of kernels launched, or -1.  partial: score_tiled_rows()*n ints.
+static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGeom g, const float *x, const float *y,
+                              const float *th, int n, int gidx0, const float *scan, const float *angle, int n_beams,
+                              int *fit, int *blk_min, long long *blk_maxkey, Extrema *ext_local,
+                              ScoreFilteredWork *wk, TiledWork *tw, int *partial, int *counters, cudaStream_t stream,
+                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
+{
+    k_bounds_reset<<<1, 32, 0, stream>>>(tw);
+    k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw);
+    k_tile_prep<<<1, 1024, 0, stream>>>(scan, angle, n_beams, g, wk, tw);
+    dim3 gt((n + kTiledGroup - 1) / kTiledGroup, kTiledY);
+    if (ev0) cudaEventRecord(ev0, stream);
+    k_score_tiled<<<gt, kTiledThreads, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+    if (ev1) cudaEventRecord(ev1, stream);
+    dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices);
+    k_score_fast<<<gf, kFastThreads, 0, stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
+                                                  partial + (size_t)kTiledY * n, counters);
+    k_score_slow<<<(n + 255) / 256, 256, 0, stream>>>(grid, g, x, y, th, n, scan, angle, wk,
+                                                      partial + (size_t)(kTiledY + kFastSlices) * n);
+    const int nblk = (n + kTile - 1) / kTile;
+    k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey);
+    k_extrema<<<1, 1024, 0, stream>>>(blk_min, blk_maxkey, nblk, x, y, th, gidx0, ext_local);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return 8;
+}
+
+}  // namespace pf

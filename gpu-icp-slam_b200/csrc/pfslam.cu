@@ -17,6 +17,7 @@
 
 #include "pf_kernels2d.cuh"
 #include "pf_score_filtered.cuh"
+#include "pf_score_tiled.cuh"
 
 using namespace pf;
 
@@ -64,10 +65,17 @@ struct pfslam_engine {
     int *counters = nullptr;
     ScoreFilteredWork *fwork = nullptr;
     int *score_partial = nullptr;
+    TiledWork *twork = nullptr;
+    CUtensorMap tmap;
+    int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
     // pinned host staging
     float *h_scan = nullptr;
     FrameResult *h_res = nullptr;
     long long launches = 0;
+    // in-step kernel timing
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_n = 0;
 };
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -89,7 +97,7 @@ void pfslam_default_config(pfslam_config *c)
     c->map_res_x = 0.025f; c->map_res_y = 0.025f;
     c->device = 0;
     c->path = PFSLAM_PATH_GRID2D;
-    c->score_mode = PFSLAM_SCORE_FILTERED;
+    c->score_mode = PFSLAM_SCORE_TILED;
     c->quirks = PFSLAM_QUIRKS_REFERENCE;
 }
 
@@ -105,8 +113,9 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->tiles_local);
     if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
-    cudaFree(e->fwork); cudaFree(e->score_partial);
+    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork);
     cudaFreeHost(e->h_scan); cudaFreeHost(e->h_res);
+    for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return PFSLAM_OK;
@@ -145,7 +154,9 @@ static int engine_alloc(pfslam_engine *e)
     CUDA_TRY(cudaMalloc(&e->res, sizeof(FrameResult)));
     CUDA_TRY(cudaMalloc(&e->counters, sizeof(int) * 8));
     CUDA_TRY(cudaMalloc(&e->fwork, sizeof(ScoreFilteredWork)));
-    CUDA_TRY(cudaMalloc(&e->score_partial, sizeof(int) * score_partial_ints(n)));
+    CUDA_TRY(cudaMalloc(&e->score_partial, sizeof(int) * (size_t)score_tiled_rows() * n));
+    CUDA_TRY(cudaMalloc(&e->twork, sizeof(TiledWork)));
+    CUDA_TRY(cudaMemsetAsync(e->twork, 0, sizeof(TiledWork), e->stream));
     CUDA_TRY(cudaMallocHost(&e->h_scan, sizeof(float) * e->cfg.n_beams));
     CUDA_TRY(cudaMallocHost(&e->h_res, sizeof(FrameResult)));
     // initial state: kernel.cu:122-132
@@ -185,7 +196,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
         return set_error(PFSLAM_ERR_ARG, "sharded engines need n_particles %% 1024 == 0 and equal shards");
     if (cfg->path != PFSLAM_PATH_GRID2D)
         return set_error(PFSLAM_ERR_UNSUPPORTED, "path %d not built yet (2D occupancy grid only)", cfg->path);
-    if (cfg->score_mode != PFSLAM_SCORE_EXACT && cfg->score_mode != PFSLAM_SCORE_FILTERED)
+    if (cfg->score_mode < PFSLAM_SCORE_EXACT || cfg->score_mode > PFSLAM_SCORE_TILED)
         return set_error(PFSLAM_ERR_ARG, "bad score_mode");
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -211,6 +222,19 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
     rc = score_filtered_setup(e->cfg.device);
     if (rc != 0) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "scoring kernel setup failed"); }
+    // the fixed-point scorers need an integral map centre c0 = 0.5*scale/res and maps below 2048 cells;
+    // the tiled scorer additionally needs a TMA-legal row stride and at most 2048 beams
+    {
+        const float c0x = (0.5f * cfg->map_scale_x) / cfg->map_res_x, c0y = (0.5f * cfg->map_scale_y) / cfg->map_res_y;
+        const bool fixed_ok = c0x == (float)(int)c0x && c0y == (float)(int)c0y && e->geom.w <= 2000 && e->geom.h <= 2000;
+        e->score_mode = cfg->score_mode;
+        if (!fixed_ok) e->score_mode = PFSLAM_SCORE_EXACT;
+        if (e->score_mode == PFSLAM_SCORE_TILED) {
+            if (cfg->n_beams > kMaxGroups * kChunkBeams || make_grid_tensor_map(&e->tmap, e->grid, e->geom.w, e->geom.h) != 0 ||
+                score_tiled_setup() != 0)
+                e->score_mode = PFSLAM_SCORE_FILTERED;
+        }
+    }
     *out = e;
     return PFSLAM_OK;
 }
@@ -263,7 +287,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     const float *scan = scan_dev ? scan_dev : e->scan;
-    if (e->cfg.score_mode == PFSLAM_SCORE_EXACT) {
+    if (e->score_mode == PFSLAM_SCORE_EXACT) {
         if (ev0) cudaEventRecord(ev0, e->stream);
         k_score_exact<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(
             e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle, e->cfg.n_beams,
@@ -274,6 +298,13 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
         k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y,
                                              e->th, e->gidx0, e->ext_local);
         e->launches++;
+    } else if (e->score_mode == PFSLAM_SCORE_TILED) {
+        int nl = score_tiled_launch(e->tmap, e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
+                                    e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
+                                    e->twork, e->score_partial, e->counters, e->stream, ev0, ev1);
+        if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
+                                     cudaGetErrorString(cudaGetLastError()));
+        e->launches += nl;
     } else {
         int nl = score_filtered_launch(e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                        e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local,
@@ -286,7 +317,43 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     return PFSLAM_OK;
 }
 
-int pfslam_phase_score(pfslam_engine *e, const float *scan_dev) { return score_phase(e, scan_dev, nullptr, nullptr); }
+int pfslam_phase_score(pfslam_engine *e, const float *scan_dev)
+{
+    if (e && e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2) {
+        const int k = e->prof_n++;
+        return score_phase(e, scan_dev, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]);
+    }
+    return score_phase(e, scan_dev, nullptr, nullptr);
+}
+
+int pfslam_profile_enable(pfslam_engine *e, int32_t on)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (on && e->prof_ev.empty()) {
+        e->prof_ev.resize(2 * 4096);
+        for (auto &ev : e->prof_ev) CUDA_TRY(cudaEventCreate(&ev));
+    }
+    e->prof_on = on != 0;
+    e->prof_n = 0;
+    return PFSLAM_OK;
+}
+
+int pfslam_profile_read(pfslam_engine *e, float *ms_kernel_mean, int32_t *n_launches)
+{
+    if (!e || !ms_kernel_mean || !n_launches) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    double tot = 0.0;
+    for (int k = 0; k < e->prof_n; k++) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]));
+        tot += ms;
+    }
+    *n_launches = e->prof_n;
+    *ms_kernel_mean = e->prof_n ? (float)(tot / e->prof_n) : 0.f;
+    e->prof_n = 0;
+    return PFSLAM_OK;
+}
 
 int pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase)
 {

@@ -18,7 +18,7 @@ import numpy as np
 from . import scans as _scans
 
 PATH_GRID2D, PATH_KD = 0, 1
-SCORE_EXACT, SCORE_FILTERED = 0, 1
+SCORE_EXACT, SCORE_FILTERED, SCORE_TILED = 0, 1, 2
 QUIRK_Q1 = 1
 QUIRKS_REFERENCE = QUIRK_Q1
 BUF_EXTREMA_LOCAL, BUF_EXTREMA_ALL, BUF_TILES_LOCAL, BUF_TILES_ALL, BUF_POSE_LOCAL, BUF_POSE_ALL, BUF_SCAN = range(7)
@@ -90,6 +90,8 @@ _SIGS = {
     "pfslam_device_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pfslam_launch_count": (C.c_int64, [C.c_void_p]),
     "pfslam_profile_score": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "pfslam_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pfslam_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pfslam_debug_trig": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
@@ -185,7 +187,7 @@ class ParticleFilter:
     """One engine (one GPU's shard of the particle cloud + a replica of the map)."""
 
     def __init__(self, n_particles=1000, scene=None, n_beams=1081, device=0,
-                 score_mode=SCORE_FILTERED, quirks=QUIRKS_REFERENCE, path=PATH_GRID2D,
+                 score_mode=SCORE_TILED, quirks=QUIRKS_REFERENCE, path=PATH_GRID2D,
                  n_particles_global=None, particle_offset=0, n_ranks=1):
         self._lib = load_library()
         self._h = C.c_void_p()
@@ -290,6 +292,15 @@ class ParticleFilter:
         a, b = C.c_float(), C.c_float()
         self._check(self._lib.pfslam_profile_score(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.pfslam_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """(mean ms of the dominant scoring kernel over the steps since enable/read, launches)"""
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self._lib.pfslam_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def update_grid(self, scan, pose):
         """PFUpdateMap alone (src/kernel.cu:551) for an explicit robot pose."""

@@ -36,6 +36,7 @@ extern "C" {
 /* scoring kernels; both produce the same integers as kernEvaluateParticles (kernel.cu:277) */
 #define PFSLAM_SCORE_EXACT    0 /* one cosf/sinf per (particle, beam), the reference's expression */
 #define PFSLAM_SCORE_FILTERED 1 /* hoisted trig + rounding guard band, exact fallback for near-ties */
+#define PFSLAM_SCORE_TILED    2 /* FILTERED + TMA-staged 128x128 grid windows in shared memory (default) */
 
 /* reference quirks reproduced by default */
 #define PFSLAM_QUIRK_Q1_HALF_WEIGHT_SYNC 1u /* kernel.cu:337: only ceil(N/2) weights persist   */
@@ -133,6 +134,12 @@ int64_t pfslam_launch_count(pfslam_engine *e);
  * CUDA events around the dominant kernel alone (k_score_fast or k_score_exact) and around the whole
  * phase; returns both durations in milliseconds after synchronising */
 int  pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase);
+
+/* in-step variant: while enabled, every scoring phase (pfslam_step, pfslam_step_async,
+ * pfslam_phase_score) brackets its dominant kernel with a CUDA event pair (ring of 4096); pfslam_profile_read
+ * synchronises, returns the mean duration in ms over the recorded launches and clears the ring */
+int  pfslam_profile_enable(pfslam_engine *e, int32_t on);
+int  pfslam_profile_read(pfslam_engine *e, float *ms_kernel_mean, int32_t *n_launches);
 
 /* test hook: libdevice cosf/sinf of n host floats evaluated on the device (the functions the
  * reference's kernels call, kernel.cu:185-186); used to validate the oracle's emulation */

@@ -64,7 +64,10 @@ def test_noise_bit_exact(oracle):
             assert np.array_equal(bits(th), bits(to))
 
 
-@pytest.mark.parametrize("mode", ["exact", "filtered"])
+MODES = {"exact": 0, "filtered": 1, "tiled": 2}
+
+
+@pytest.mark.parametrize("mode", ["exact", "filtered", "tiled"])
 @pytest.mark.parametrize("case", ["near_origin", "spread", "edge_of_map"])
 def test_score_bit_exact(oracle, scans, mode, case):
     """kernEvaluateParticles parity on a dense pseudo-random grid (every cell nonzero-ish, so any
@@ -79,8 +82,7 @@ def test_score_bit_exact(oracle, scans, mode, case):
     else:
         x, y, th = helpers.synth_particles(n, salt=3, spread=1.0, spread_th=3.0, center=(19.5, -19.5, 0.0))
     cfg = helpers.ocfg(TRIG_CUDA, MAD_FUSED)
-    sm = g.SCORE_EXACT if mode == "exact" else g.SCORE_FILTERED
-    with g.ParticleFilter(n, score_mode=sm) as pf:
+    with g.ParticleFilter(n, score_mode=MODES[mode]) as pf:
         pf.set_grid(grid)
         pf.set_particles(x, y, th, np.ones(n, np.float32))
         for f in (1, 60, 200):
@@ -107,7 +109,7 @@ def test_score_special_ranges(oracle):
     cfg = helpers.ocfg(TRIG_CUDA, MAD_FUSED)
     fo = np.zeros(n, np.int32)
     oracle.pfo_score2d_many(C.byref(cfg), P(grid, helpers.bp), P(x), P(y), P(th), n, P(sc), P(fo, helpers.ip))
-    for sm in (g.SCORE_EXACT, g.SCORE_FILTERED):
+    for sm in (g.SCORE_EXACT, g.SCORE_FILTERED, g.SCORE_TILED):
         with g.ParticleFilter(n, score_mode=sm) as pf:
             pf.set_grid(grid)
             pf.set_particles(x, y, th, np.ones(n, np.float32))
@@ -137,16 +139,15 @@ def test_update_grid_bit_exact(oracle, scans):
             assert np.array_equal(pf.get_grid().reshape(-1), go), "pose %r" % (pose,)
 
 
-@pytest.mark.parametrize("n,mode,q1", [(1000, "filtered", 1), (1000, "exact", 1), (4096, "filtered", 0), (777, "filtered", 1)])
+@pytest.mark.parametrize("n,mode,q1", [(1000, "tiled", 1), (1000, "filtered", 1), (1000, "exact", 1), (4096, "tiled", 0), (777, "tiled", 1), (5000, "tiled", 1)])
 def test_free_running_step_bit_exact(scans, n, mode, q1):
     """The whole 2D step, free-running from the initial state over the fixture frames: pose, score
     extrema, arg-max, Neff, resample decision, map-cell counts every frame; particles, weights and
     the full grid at checkpoints.  No teacher forcing: one differing bit anywhere would diverge."""
     g = _gpu()
-    frames = 120 if n <= 1000 else 60
+    frames = 120 if n <= 1000 else 50
     of = helpers.OracleFilter(n, helpers.ocfg(TRIG_CUDA, MAD_FUSED, q1=q1))
-    sm = g.SCORE_EXACT if mode == "exact" else g.SCORE_FILTERED
-    with g.ParticleFilter(n, score_mode=sm, quirks=(g.QUIRK_Q1 if q1 else 0)) as pf:
+    with g.ParticleFilter(n, score_mode=MODES[mode], quirks=(g.QUIRK_Q1 if q1 else 0)) as pf:
         n_resampled = 0
         for f in range(1, frames + 1):
             r = pf.step(scans[f], f)
