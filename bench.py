@@ -211,7 +211,9 @@ def run_ours(args):
     n = args.particles
     K, W = args.steps, max(args.warmup, 3)
     scans, order = workload_scans(K + W + 8)
-    stream = torch.cuda.current_stream()
+    # everything runs on one non-default stream (the legacy default stream cannot be graph-captured)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     if world > 1:
         from gpu_icp_slam_b200.dist import ShardedParticleFilter

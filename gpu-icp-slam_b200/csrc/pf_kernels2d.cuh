@@ -29,6 +29,14 @@ struct FrameResult {
     int   resampled, n_free, n_wall, n_slow;
 };
 
+// per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
+// step can be replayed with new values (a 16-byte H2D copy node at the head of the graph)
+struct StepParams {
+    const float *scan;   // this frame's ranges (device)
+    int frame;           // frame number (seeds, kernel.cu:380, :434)
+    int pad;
+};
+
 // extrema record exchanged between ranks: 8 words
 struct Extrema {
     int   fit_min, fit_max, best_gidx;
@@ -40,11 +48,12 @@ struct Extrema {
 // motion: kernel.cu:375-397 ParticleAddNoise; device evaluation order of
 // glm::vec3 noise(distx(e2), disty(e2), distt(e2)) is x, y, theta (read off the reference SASS).
 __global__ void __launch_bounds__(256)
-k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n, int frame,
-         int gidx0)
+k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
+         const StepParams *__restrict__ sp, int gidx0)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int frame = sp->frame;
     uint32_t st = pf_minstd_seed(pf_seed(frame, gidx0 + i, 0));
     float nx = pf_normal(st, 0.015f);
     float ny = pf_normal(st, 0.015f);
@@ -96,10 +105,11 @@ __device__ __forceinline__ long long extrema_key(int fit, int gidx)
 __global__ void __launch_bounds__(256)
 k_score_exact(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict__ x,
               const float *__restrict__ y, const float *__restrict__ th, int n, int gidx0,
-              const float *__restrict__ scan, const float *__restrict__ angle, int n_beams,
+              const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
               int *__restrict__ fit, int *__restrict__ blk_min, long long *__restrict__ blk_maxkey)
 {
     __shared__ int part[8][32];
+    const float *__restrict__ scan = sp->scan;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + lane;
     const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
@@ -308,12 +318,13 @@ k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restri
 __global__ void __launch_bounds__(256)
 k_resample(const FrameResult *__restrict__ res, const float *__restrict__ prefix,
            const float *__restrict__ tiles_all, int n_tiles_local, long long tiles_block_floats,
-           const float *__restrict__ pose_all, int n_local, int n_global, int gidx0, int frame,
-           float *__restrict__ x, float *__restrict__ y, float *__restrict__ th,
-           float *__restrict__ w)
+           const float *__restrict__ pose_all, int n_local, int n_global, int gidx0,
+           const StepParams *__restrict__ sp, float *__restrict__ x, float *__restrict__ y,
+           float *__restrict__ th, float *__restrict__ w)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local || !res->resampled) return;
+    const int frame = sp->frame;
     const int nt = (n_global + kTile - 1) / kTile;   // == n_ranks * n_tiles_local when sharded
     uint32_t st = pf_minstd_seed(pf_seed((int)res->neff, frame, gidx0 + i));
     uint32_t u = pf_minstd_next(st) - 1u;
@@ -374,9 +385,10 @@ __device__ __forceinline__ int8_t clamp_add(int8_t v, int d)
 // The first thread to set a cell's bit this frame applies the -1 (== the reference's bool mask).
 __global__ void __launch_bounds__(128)
 k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
-           const float *__restrict__ scan, const float *__restrict__ angle,
+           const StepParams *__restrict__ sp, const float *__restrict__ angle,
            unsigned *__restrict__ free_bits, int *__restrict__ counters)
 {
+    const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
     int cx, cy; center_cell(g, res->pose[0], res->pose[1], cx, cy);
     float wx, wy;
@@ -413,9 +425,10 @@ k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__
 // +4 lands on top of the -1 exactly like the reference's two kernUpdateMap launches.
 __global__ void __launch_bounds__(128)
 k_map_wall(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
-           const float *__restrict__ scan, const float *__restrict__ angle, int n_beams,
+           const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
            unsigned *__restrict__ wall_bits, int *__restrict__ counters)
 {
+    const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;
     if (j < n_beams) {

@@ -45,9 +45,10 @@ inline int score_partial_count(int n) { return (n + 31) / 32 > (n + kTile - 1) /
 
 // Per-frame beam preparation: classify, compact, and compute the per-beam constants in double.
 __global__ void __launch_bounds__(1024)
-k_beam_prep(const float *__restrict__ scan, const float *__restrict__ angle, int n_beams, MapGeom g,
+k_beam_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams, MapGeom g,
             ScoreFilteredWork *__restrict__ wk)
 {
+    const float *__restrict__ scan = sp->scan;
     __shared__ int s_warp[32];
     __shared__ int s_base_f, s_base_s;
     if (threadIdx.x == 0) { s_base_f = 0; s_base_s = 0; }
@@ -93,10 +94,11 @@ k_beam_prep(const float *__restrict__ scan, const float *__restrict__ angle, int
 __global__ void __launch_bounds__(kFastThreads)
 k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict__ x,
              const float *__restrict__ y, const float *__restrict__ th, int n,
-             const float *__restrict__ scan, const float *__restrict__ angle, int n_beams,
+             const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
              const ScoreFilteredWork *__restrict__ wk, int *__restrict__ partial,
              int *__restrict__ counters)
 {
+    const float *__restrict__ scan = sp->scan;
     __shared__ float4 s_const[(kMaxBeams + kFastSlices - 1) / kFastSlices];
     __shared__ unsigned s_queue[kQueueCap];
     __shared__ float s_pose[3][kFastThreads];
@@ -178,9 +180,10 @@ k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict
 __global__ void __launch_bounds__(256)
 k_score_slow(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict__ x,
              const float *__restrict__ y, const float *__restrict__ th, int n,
-             const float *__restrict__ scan, const float *__restrict__ angle,
+             const StepParams *__restrict__ sp, const float *__restrict__ angle,
              const ScoreFilteredWork *__restrict__ wk, int *__restrict__ partial_slow)
 {
+    const float *__restrict__ scan = sp->scan;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int ns = wk->ns;
@@ -237,7 +240,7 @@ inline size_t score_partial_ints(int n) { return (size_t)(kFastSlices + 1) * n; 
 
 // returns the number of kernels launched, or -1.  partial: score_partial_ints(n) ints of scratch.
 static int score_filtered_launch(const int8_t *grid, MapGeom g, const float *x, const float *y,
-                                 const float *th, int n, int gidx0, const float *scan,
+                                 const float *th, int n, int gidx0, const StepParams *scan,
                                  const float *angle, int n_beams, int *fit, int *blk_min,
                                  long long *blk_maxkey, Extrema *ext_local, ScoreFilteredWork *wk,
                                  int *partial, int *counters, cudaStream_t stream,

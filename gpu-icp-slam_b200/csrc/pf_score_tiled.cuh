@@ -118,9 +118,10 @@ __device__ __forceinline__ void trig_range(double p0, double p1, double &cmin, d
 //   tiled (conservative hit box fits its chunk's 128x128 window)    -> tw chunks  (k_score_tiled)
 //   wide  (fast domain, but does not fit)                           -> wk->fconst (k_score_fast)
 __global__ void __launch_bounds__(1024)
-k_tile_prep(const float *__restrict__ scan, const float *__restrict__ angle, int n_beams, MapGeom g,
+k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams, MapGeom g,
             ScoreFilteredWork *__restrict__ wk, TiledWork *__restrict__ tw)
 {
+    const float *__restrict__ scan = sp->scan;
     __shared__ int s_scan[32];
     __shared__ int4 s_box[2048];
     __shared__ int s_j[2048];
@@ -323,9 +324,10 @@ struct TiledSmem {
 __global__ void __launch_bounds__(kTiledThreads)
 k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
               const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
-              const float *__restrict__ scan, const float *__restrict__ angle,
+              const StepParams *__restrict__ sp, const float *__restrict__ angle,
               const TiledWork *__restrict__ tw, int *__restrict__ partial, int *__restrict__ counters)
 {
+    const float *__restrict__ scan = sp->scan;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -540,7 +542,7 @@ static int score_tiled_setup()
 
 // returns the number of kernels launched, or -1.  partial: score_tiled_rows()*n ints.
 static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGeom g, const float *x, const float *y,
-                              const float *th, int n, int gidx0, const float *scan, const float *angle, int n_beams,
+                              const float *th, int n, int gidx0, const StepParams *scan, const float *angle, int n_beams,
                               int *fit, int *blk_min, long long *blk_maxkey, Extrema *ext_local,
                               ScoreFilteredWork *wk, TiledWork *tw, int *partial, int *counters, cudaStream_t stream,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)

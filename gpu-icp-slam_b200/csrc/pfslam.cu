@@ -72,6 +72,19 @@ struct pfslam_engine {
     float *h_scan = nullptr;
     FrameResult *h_res = nullptr;
     long long launches = 0;
+    // per-step parameters (device copy + pinned ring) and the captured step graph
+    StepParams *sp = nullptr;
+    StepParams *h_sp = nullptr;            // kParamSlots pinned slots
+    StepParams cur{};                      // what the device copy will hold once the stream drains
+    unsigned long long n_param_pushes = 0;
+    cudaEvent_t lap_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphNode_t graph_param_node = nullptr;
+    bool graph_failed = false;
+    bool use_graph = true;
+    int graph_kernels = 0;
+    bool in_capture = false;
     // in-step kernel timing
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -79,6 +92,38 @@ struct pfslam_engine {
 };
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+constexpr int kParamSlots = 256;
+
+// next pinned parameter slot; slots are recycled after a full lap, guarded by one event per quarter lap
+static int next_param_slot(pfslam_engine *e, StepParams **slot)
+{
+    const int s = (int)(e->n_param_pushes % kParamSlots);
+    if (s % (kParamSlots / 4) == 0 && e->n_param_pushes >= (unsigned long long)kParamSlots)
+        CUDA_TRY(cudaEventSynchronize(e->lap_ev[s / (kParamSlots / 4)]));
+    *slot = &e->h_sp[s];
+    return PFSLAM_OK;
+}
+static int param_slot_used(pfslam_engine *e)
+{
+    const int s = (int)(e->n_param_pushes % kParamSlots);
+    e->n_param_pushes++;
+    if (s % (kParamSlots / 4) == kParamSlots / 4 - 1) CUDA_TRY(cudaEventRecord(e->lap_ev[s / (kParamSlots / 4)], e->stream));
+    return PFSLAM_OK;
+}
+
+// make the device StepParams equal (scan, frame) for the kernels enqueued after this call
+static int push_params(pfslam_engine *e, const float *scan, int frame)
+{
+    if (e->in_capture) return PFSLAM_OK;       // the graph's own copy node does it
+    if (e->cur.scan == scan && e->cur.frame == frame && e->n_param_pushes) return PFSLAM_OK;
+    StepParams *slot = nullptr;
+    int rc = next_param_slot(e, &slot);
+    if (rc) return rc;
+    slot->scan = scan; slot->frame = frame; slot->pad = 0;
+    CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
+    e->cur = *slot;
+    return param_slot_used(e);
+}
 
 extern "C" {
 
@@ -113,7 +158,11 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->tiles_local);
     if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
-    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork);
+    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->sp);
+    cudaFreeHost(e->h_sp);
+    for (auto ev : e->lap_ev) if (ev) cudaEventDestroy(ev);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->graph) cudaGraphDestroy(e->graph);
     cudaFreeHost(e->h_scan); cudaFreeHost(e->h_res);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -157,6 +206,10 @@ static int engine_alloc(pfslam_engine *e)
     CUDA_TRY(cudaMalloc(&e->score_partial, sizeof(int) * (size_t)score_tiled_rows() * n));
     CUDA_TRY(cudaMalloc(&e->twork, sizeof(TiledWork)));
     CUDA_TRY(cudaMemsetAsync(e->twork, 0, sizeof(TiledWork), e->stream));
+    CUDA_TRY(cudaMalloc(&e->sp, sizeof(StepParams)));
+    CUDA_TRY(cudaMemsetAsync(e->sp, 0, sizeof(StepParams), e->stream));
+    CUDA_TRY(cudaMallocHost(&e->h_sp, sizeof(StepParams) * kParamSlots));
+    for (auto &ev : e->lap_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost(&e->h_scan, sizeof(float) * e->cfg.n_beams));
     CUDA_TRY(cudaMallocHost(&e->h_res, sizeof(FrameResult)));
     // initial state: kernel.cu:122-132
@@ -246,6 +299,8 @@ int pfslam_set_stream(pfslam_engine *e, void *cuda_stream)
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
     e->stream = (cudaStream_t)cuda_stream;
+    // the legacy default stream cannot be captured into a graph: plain launches there
+    e->use_graph = cuda_stream != nullptr && cuda_stream != (void *)cudaStreamLegacy;
     return PFSLAM_OK;
 }
 
@@ -272,7 +327,8 @@ int pfslam_upload_scan(pfslam_engine *e, const float *scan_host)
 int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
-    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, frame, e->gidx0);
+    { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
+    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     if (e->n_ranks == 1) {
@@ -286,7 +342,8 @@ int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
 static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
-    const float *scan = scan_dev ? scan_dev : e->scan;
+    { int rc = push_params(e, scan_dev ? scan_dev : e->scan, e->cur.frame); if (rc) return rc; }
+    const StepParams *scan = e->sp;
     if (e->score_mode == PFSLAM_SCORE_EXACT) {
         if (ev0) cudaEventRecord(ev0, e->stream);
         k_score_exact<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(
@@ -395,8 +452,9 @@ static int launch_prefix(pfslam_engine *e)
     return PFSLAM_OK;
 }
 
-static int launch_map(pfslam_engine *e, const float *scan)
+static int launch_map(pfslam_engine *e)
 {
+    const StepParams *scan = e->sp;
     CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, e->stream));
     k_map_free<<<e->cfg.n_beams, 128, 0, e->stream>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
@@ -416,20 +474,70 @@ static int launch_map(pfslam_engine *e, const float *scan)
 int pfslam_phase_map(pfslam_engine *e, const float *scan_dev)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
-    int rc = launch_prefix(e);
+    int rc = push_params(e, scan_dev ? scan_dev : e->scan, e->cur.frame);
     if (rc) return rc;
-    return launch_map(e, scan_dev ? scan_dev : e->scan);
+    if ((rc = launch_prefix(e))) return rc;
+    return launch_map(e);
 }
 
 int pfslam_phase_resample(pfslam_engine *e, int32_t frame)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
     k_resample<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->res, e->prefix, e->tiles_all, e->n_tiles,
                                                            e->tiles_block, e->pose_all, e->n, e->n_global,
-                                                           e->gidx0, frame, e->x, e->y, e->th, e->w);
+                                                           e->gidx0, e->sp, e->x, e->y, e->th, e->w);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
+}
+
+static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
+{
+    int rc;
+    if ((rc = pfslam_phase_motion(e, frame))) return rc;
+    if ((rc = pfslam_phase_score(e, scan_dev))) return rc;
+    if ((rc = pfslam_phase_weights(e))) return rc;
+    if ((rc = pfslam_phase_map(e, scan_dev))) return rc;
+    if ((rc = pfslam_phase_resample(e, frame))) return rc;
+    return PFSLAM_OK;
+}
+
+// Capture the whole single-GPU step once; every later step is one cudaGraphLaunch whose head node
+// copies that step's {scan pointer, frame} from a pinned slot into the device StepParams.
+static int build_graph(pfslam_engine *e)
+{
+    const long long launches_before = e->launches;
+    if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cudaMemcpyAsync(e->sp, &e->h_sp[0], sizeof(StepParams), cudaMemcpyHostToDevice, e->stream);
+    e->in_capture = true;
+    int rc = run_phases(e, nullptr, 0);
+    e->in_capture = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    e->launches = launches_before;
+    if (rc != PFSLAM_OK || ce != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return -1; }
+    size_t nn = 0;
+    cudaGraphGetNodes(g, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(g, nodes.data(), &nn);
+    cudaGraphNode_t pn = nullptr;
+    int n_kernels = 0;
+    for (auto nd : nodes) {
+        cudaGraphNodeType ty;
+        cudaGraphNodeGetType(nd, &ty);
+        if (ty == cudaGraphNodeTypeKernel) n_kernels++;
+        if (ty == cudaGraphNodeTypeMemcpy) {
+            cudaMemcpy3DParms mp;
+            if (cudaGraphMemcpyNodeGetParams(nd, &mp) == cudaSuccess && mp.dstPtr.ptr == (void *)e->sp) pn = nd;
+        }
+    }
+    if (!pn) { cudaGraphDestroy(g); return -1; }
+    cudaGraphExec_t ge = nullptr;
+    if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); return -1; }
+    e->graph = g; e->graph_exec = ge; e->graph_param_node = pn;
+    e->graph_kernels = n_kernels;
+    return 0;
 }
 
 int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
@@ -438,13 +546,26 @@ int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
     if (e->n_ranks != 1)
         return set_error(PFSLAM_ERR_STATE, "sharded engines are stepped phase by phase by the multi-GPU host");
     CUDA_TRY(cudaSetDevice(e->cfg.device));
-    int rc;
-    if ((rc = pfslam_phase_motion(e, frame))) return rc;
-    if ((rc = pfslam_phase_score(e, scan_dev))) return rc;
-    if ((rc = pfslam_phase_weights(e))) return rc;
-    if ((rc = pfslam_phase_map(e, scan_dev))) return rc;
-    if ((rc = pfslam_phase_resample(e, frame))) return rc;
-    return PFSLAM_OK;
+    const float *scan = scan_dev ? scan_dev : e->scan;
+    if (e->use_graph && !e->prof_on && !e->graph_failed) {
+        if (!e->graph_exec && build_graph(e) != 0) e->graph_failed = true;
+        if (e->graph_exec) {
+            StepParams *slot = nullptr;
+            int rc = next_param_slot(e, &slot);
+            if (rc) return rc;
+            slot->scan = scan; slot->frame = frame; slot->pad = 0;
+            CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(e->graph_exec, e->graph_param_node, e->sp, slot,
+                                                        sizeof(StepParams), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaGraphLaunch(e->graph_exec, e->stream));
+            e->cur = *slot;
+            e->launches += e->graph_kernels;
+            return param_slot_used(e);
+        }
+    }
+    // plain launches (profiling, or graph capture unavailable on this stream)
+    int rc = push_params(e, scan, frame);
+    if (rc) return rc;
+    return run_phases(e, scan_dev, frame);
 }
 
 static void copy_result(const FrameResult *r, pfslam_frame_result *out)
@@ -495,7 +616,8 @@ int pfslam_update_grid(pfslam_engine *e, const float *scan_host, const float pos
     memset(e->h_res, 0, sizeof(FrameResult));
     e->h_res->pose[0] = pose[0]; e->h_res->pose[1] = pose[1]; e->h_res->pose[2] = pose[2];
     CUDA_TRY(cudaMemcpyAsync(e->res, e->h_res, sizeof(FrameResult), cudaMemcpyHostToDevice, e->stream));
-    if ((rc = launch_map(e, e->scan))) return rc;
+    if ((rc = push_params(e, e->scan, e->cur.frame))) return rc;
+    if ((rc = launch_map(e))) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PFSLAM_OK;
 }

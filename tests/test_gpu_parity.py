@@ -167,6 +167,25 @@ def test_free_running_step_bit_exact(scans, n, mode, q1):
     of.close()
 
 
+def test_graph_and_plain_launch_paths_agree(scans):
+    """the captured-graph step (default) and the plain-launch step (used while profiling) are the
+    same computation"""
+    g = _gpu()
+    n = 2048
+    with g.ParticleFilter(n) as a, g.ParticleFilter(n) as b:
+        b.profile_enable(True)                  # forces plain launches
+        for f in range(1, 40):
+            ra, rb = a.step(scans[f], f), b.step(scans[f], f)
+            assert np.array_equal(bits(list(ra.pose)), bits(list(rb.pose))) and ra.best_index == rb.best_index
+            assert ra.neff == rb.neff and ra.resampled == rb.resampled
+        ms, cnt = b.profile_read()
+        assert cnt == 39 and ms > 0
+        assert np.array_equal(a.get_grid(), b.get_grid())
+        xa, xb = a.get_particles(), b.get_particles()
+        assert all(np.array_equal(bits(u), bits(v)) for u, v in zip(xa, xb))
+        assert a.launch_count > 39 * 10
+
+
 def test_reference_named_interface(scans):
     """particleFilterInit / particleFilter / getPCData / particleFilterFree call contract (main.cpp:175-237)"""
     g = _gpu()
