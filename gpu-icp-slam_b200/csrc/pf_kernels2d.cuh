@@ -47,20 +47,51 @@ struct Extrema {
 // ---------------------------------------------------------------------------------------------
 // motion: kernel.cu:375-397 ParticleAddNoise; device evaluation order of
 // glm::vec3 noise(distx(e2), disty(e2), distt(e2)) is x, y, theta (read off the reference SASS).
+__device__ __forceinline__ int float_order(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float order_float(int k)
+{
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+// Also reduces the post-noise pose bounds of the cloud (ordered-int min/max of x, y, theta) into
+// bounds[6] for the tiled scorer's window placement.
 __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
-         const StepParams *__restrict__ sp, int gidx0)
+         const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds)
 {
+    __shared__ int s_b[6];
+    if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int frame = sp->frame;
-    uint32_t st = pf_minstd_seed(pf_seed(frame, gidx0 + i, 0));
-    float nx = pf_normal(st, 0.015f);
-    float ny = pf_normal(st, 0.015f);
-    float nt = pf_normal(st, 0.01f);
-    x[i] = __fadd_rn(x[i], nx);
-    y[i] = __fadd_rn(y[i], ny);
-    th[i] = __fadd_rn(th[i], nt);
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    if (i < n) {
+        const int frame = sp->frame;
+        uint32_t st = pf_minstd_seed(pf_seed(frame, gidx0 + i, 0));
+        float nx = pf_normal(st, 0.015f);
+        float ny = pf_normal(st, 0.015f);
+        float nt = pf_normal(st, 0.01f);
+        const float vx = __fadd_rn(x[i], nx), vy = __fadd_rn(y[i], ny), vt = __fadd_rn(th[i], nt);
+        x[i] = vx; y[i] = vy; th[i] = vt;
+        lo[0] = hi[0] = float_order(vx); lo[1] = hi[1] = float_order(vy); lo[2] = hi[2] = float_order(vt);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_b[2 * c], lo[c]); atomicMax(&s_b[2 * c + 1], hi[c]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        if (threadIdx.x & 1) atomicMax(&bounds[threadIdx.x], s_b[threadIdx.x]);
+        else atomicMin(&bounds[threadIdx.x], s_b[threadIdx.x]);
+    }
 }
 
 __global__ void k_debug_trig(const float *__restrict__ x, long long n, float *__restrict__ c,
@@ -380,19 +411,24 @@ __device__ __forceinline__ int8_t clamp_add(int8_t v, int d)
     return (int8_t)(t < -kClamp ? -kClamp : t > kClamp ? kClamp : t);
 }
 
-// free cells: block = one beam, threads stride over the Bresenham steps.  Step k of traceRay is
-// closed-form: x = sx+k, y = sy + ystep*m_k, m_k = max(0, ceil((k*deltay - deltax/2)/deltax)).
+// Map update, free cells: block = one beam, threads stride over the Bresenham steps.  Step k of
+// traceRay is closed-form: x = sx+k, y = sy + ystep*m_k, m_k = max(0, ceil((k*deltay - deltax/2)/deltax)).
 // The first thread to set a cell's bit this frame applies the -1 (== the reference's bool mask).
+// Each thread issues the bit-set atomics of up to 8 steps before touching the grid so their
+// latencies overlap.
 __global__ void __launch_bounds__(128)
 k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle,
            unsigned *__restrict__ free_bits, int *__restrict__ counters)
 {
+    __shared__ int s_cnt;
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
     int cx, cy; center_cell(g, res->pose[0], res->pose[1], cx, cy);
     float wx, wy;
     int mine = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     if (beam_hit(g, res->pose, cx, cy, angle[j], scan[j], wx, wy)) {
         int sx = cx, sy = cy, ex = (int)wx, ey = (int)wy;
         const bool steep = abs(ey - sy) > abs(ex - sx);
@@ -401,30 +437,39 @@ k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__
         if (sx > ex) { t = sx; sx = ex; ex = t; t = sy; sy = ey; ey = t; }
         const int deltax = ex - sx, deltay = abs(ey - sy), e0 = deltax / 2;
         const int ystep = ey > sy ? 1 : -1;
-        for (int k = threadIdx.x; k < deltax; k += blockDim.x) {
-            int num = k * deltay - e0;
-            int m = num > 0 ? (num + deltax - 1) / deltax : 0;
-            int xx = sx + k, yy = sy + ystep * m;
-            int idx = steep ? yy * g.w + xx : xx * g.w + yy;
-            if (xx < g.w && yy < g.h && xx >= 0 && yy >= 0 && idx < g.w * g.h) {
-                unsigned bit = 1u << (idx & 31);
-                unsigned old = atomicOr(&free_bits[idx >> 5], bit);
-                if (!(old & bit)) { grid[idx] = clamp_add(grid[idx], kFreeWeight); mine++; }
+        for (int k0 = threadIdx.x; k0 < deltax; k0 += 8 * blockDim.x) {
+            int idx[8]; bool first[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + u * blockDim.x;
+                first[u] = false; idx[u] = 0;
+                if (k < deltax) {
+                    int num = k * deltay - e0;
+                    int m = num > 0 ? (num + deltax - 1) / deltax : 0;
+                    int xx = sx + k, yy = sy + ystep * m;
+                    int id = steep ? yy * g.w + xx : xx * g.w + yy;
+                    if (xx < g.w && yy < g.h && xx >= 0 && yy >= 0 && id < g.w * g.h) {
+                        unsigned bit = 1u << (id & 31);
+                        unsigned old = atomicOr(&free_bits[id >> 5], bit);
+                        first[u] = !(old & bit); idx[u] = id;
+                    }
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (first[u]) { grid[idx[u]] = clamp_add(grid[idx[u]], kFreeWeight); mine++; }
         }
     }
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     if (mine) atomicAdd(&s_cnt, mine);
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&counters[0], s_cnt);
 }
 
-// wall cells: one thread per beam; runs after k_map_free has completed (stream order), so the
-// +4 lands on top of the -1 exactly like the reference's two kernUpdateMap launches.
+// wall cells: one thread per beam; runs after k_map_free has completed (stream order), so the +4
+// lands on top of the -1 exactly like the reference's two kernUpdateMap launches.  The last block
+// publishes the frame's cell counters.
 __global__ void __launch_bounds__(128)
-k_map_wall(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
+k_map_wall(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
            unsigned *__restrict__ wall_bits, int *__restrict__ counters)
 {
@@ -444,13 +489,15 @@ k_map_wall(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__
         }
     }
     int c = __syncthreads_count(mine);
-    if (threadIdx.x == 0 && c) atomicAdd(&counters[1], c);
-}
-
-__global__ void k_finish_counters(FrameResult *__restrict__ res, int *__restrict__ counters)
-{
-    res->n_free = counters[0]; res->n_wall = counters[1]; res->n_slow = counters[2];
-    counters[0] = 0; counters[1] = 0; counters[2] = 0;
+    if (threadIdx.x == 0) {
+        if (c) atomicAdd(&counters[1], c);
+        __threadfence();
+        if (atomicAdd(&counters[3], 1) == (int)gridDim.x - 1) {
+            res->n_free = atomicAdd(&counters[0], 0); res->n_wall = atomicAdd(&counters[1], 0);
+            res->n_slow = atomicAdd(&counters[2], 0);
+            counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
+        }
+    }
 }
 
 }  // namespace pf

@@ -53,16 +53,6 @@ struct TiledWork {
     int bounds[8];                             // cloud bounds as ordered ints: xmin,xmax,ymin,ymax,tmin,tmax
 };
 
-__device__ __forceinline__ int float_order(float f)
-{
-    int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float order_float(int k)
-{
-    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
-}
-
 __global__ void k_bounds_reset(TiledWork *__restrict__ tw)
 {
     if (threadIdx.x < 3) { tw->bounds[2 * threadIdx.x] = 0x7fffffff; tw->bounds[2 * threadIdx.x + 1] = (int)0x80000000; }
@@ -99,18 +89,27 @@ k_cloud_bounds(const float *__restrict__ x, const float *__restrict__ y, const f
     }
 }
 
-// range of cos / sin over the angle interval [p0, p1]
-__device__ __forceinline__ void trig_range(double p0, double p1, double &cmin, double &cmax, double &smin, double &smax)
+// range of cos / sin over the angle interval [p0, p1] (float; the caller pads the box by whole cells)
+__device__ __forceinline__ void trig_range(float p0, float p1, float &cmin, float &cmax, float &smin, float &smax)
 {
-    const double PI = 3.14159265358979323846;
-    double c0 = cos(p0), c1 = cos(p1), s0 = sin(p0), s1 = sin(p1);
-    cmin = fmin(c0, c1); cmax = fmax(c0, c1); smin = fmin(s0, s1); smax = fmax(s0, s1);
-    if (!(p1 - p0 < 6.0)) { cmin = smin = -1.0; cmax = smax = 1.0; return; }
-    // extrema: cos = +1 at 2k*pi, -1 at (2k+1)*pi; sin = +1 at pi/2 + 2k*pi, -1 at -pi/2 + 2k*pi
-    if (floor(p1 / (2 * PI)) > floor(p0 / (2 * PI)) || p0 == 0.0) cmax = 1.0;
-    if (floor((p1 - PI) / (2 * PI)) > floor((p0 - PI) / (2 * PI))) cmin = -1.0;
-    if (floor((p1 - PI / 2) / (2 * PI)) > floor((p0 - PI / 2) / (2 * PI))) smax = 1.0;
-    if (floor((p1 + PI / 2) / (2 * PI)) > floor((p0 + PI / 2) / (2 * PI))) smin = -1.0;
+    const float PI = 3.14159265358979323846f, I2PI = 0.15915494309189535f;
+    float s0, c0, s1, c1;
+    sincosf(p0, &s0, &c0); sincosf(p1, &s1, &c1);
+    const float e = 2e-6f;                                  // covers sincosf error and angle rounding
+    cmin = fminf(c0, c1) - e; cmax = fmaxf(c0, c1) + e; smin = fminf(s0, s1) - e; smax = fmaxf(s0, s1) + e;
+    if (!(p1 - p0 < 6.0f)) { cmin = smin = -1.0f; cmax = smax = 1.0f; return; }
+    // extrema inside the interval: cos = +1 at 2k*pi, -1 at (2k+1)*pi; sin = +-1 at +-pi/2 + 2k*pi
+    if (floorf(p1 * I2PI) > floorf(p0 * I2PI)) cmax = 1.0f;
+    if (floorf((p1 - PI) * I2PI) > floorf((p0 - PI) * I2PI)) cmin = -1.0f;
+    if (floorf((p1 - 0.5f * PI) * I2PI) > floorf((p0 - 0.5f * PI) * I2PI)) smax = 1.0f;
+    if (floorf((p1 + 0.5f * PI) * I2PI) > floorf((p0 + 0.5f * PI) * I2PI)) smin = -1.0f;
+}
+
+// cos / sin of the (fixed) beam angles in double, computed once per engine
+__global__ void k_init_beam_trig(const float *__restrict__ angle, int n_beams, double2 *__restrict__ cs)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_beams) { double a = (double)angle[j]; cs[j] = make_double2(cos(a), sin(a)); }
 }
 
 // Per-frame preparation (one block, 1024 threads, up to 2048 beams): classify every beam as
@@ -118,7 +117,8 @@ __device__ __forceinline__ void trig_range(double p0, double p1, double &cmin, d
 //   tiled (conservative hit box fits its chunk's 128x128 window)    -> tw chunks  (k_score_tiled)
 //   wide  (fast domain, but does not fit)                           -> wk->fconst (k_score_fast)
 __global__ void __launch_bounds__(1024)
-k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams, MapGeom g,
+k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
+            const double2 *__restrict__ angle_cs, int n_beams, MapGeom g,
             ScoreFilteredWork *__restrict__ wk, TiledWork *__restrict__ tw)
 {
     const float *__restrict__ scan = sp->scan;
@@ -126,6 +126,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, 
     __shared__ int4 s_box[2048];
     __shared__ int s_j[2048];
     __shared__ int s_nelig, s_nslow, s_nwide;
+    __shared__ int s_cnt2[kMaxChunks];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) { s_nwide = 0; }
     const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
@@ -155,10 +156,11 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, 
             if (fast) {
                 elig[k] = true;
                 if (cloud_ok) {
-                    double cmin, cmax, smin, smax;
-                    const double a = (double)angle[j];
-                    trig_range(a + tmin - 1e-6, a + tmax + 1e-6, cmin, cmax, smin, smax);
-                    const double xa = rx * cmin, xb = rx * cmax, ya = ry * smin, yb = ry * smax;
+                    float cmin, cmax, smin, smax;
+                    const float a = angle[j];
+                    // interval of rot = angle + theta over the cloud, padded for float rounding
+                    trig_range(a + (float)tmin - 4e-6f, a + (float)tmax + 4e-6f, cmin, cmax, smin, smax);
+                    const double xa = rx * (double)cmin, xb = rx * (double)cmax, ya = ry * (double)smin, yb = ry * (double)smax;
                     const double vx0 = (double)c0x + pxmin / (double)g.res_x + fmin(xa, xb);
                     const double vx1 = (double)c0x + pxmax / (double)g.res_x + fmax(xa, xb);
                     const double vy0 = (double)c0y + pymin / (double)g.res_y + fmin(ya, yb);
@@ -204,10 +206,11 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, 
         int j = 0;
         if (have) {
             j = s_j[d];
-            const double r = (double)scan[j], a = (double)angle[j];
-            rx = r / (double)g.res_x; ry = r / (double)g.res_y; ca = cos(a); sa = sin(a);
+            const double r = (double)scan[j];
+            const double2 t2 = angle_cs[j];
+            rx = r / (double)g.res_x; ry = r / (double)g.res_y; ca = t2.x; sa = t2.y;
         }
-        if (lane == 0) { tw->chunk[2 * c].count = 0; tw->chunk[2 * c + 1].count = 0; }
+        if (lane == 0) { tw->chunk[2 * c].count = 0; tw->chunk[2 * c + 1].count = 0; s_cnt2[2 * c] = 0; s_cnt2[2 * c + 1] = 0; }
         __syncwarp();
         for (int pass = 0; pass < 2; pass++) {
             int x0 = todo ? b.x : 0x3fffffff, x1 = todo ? b.y : -0x3fffffff;
@@ -243,7 +246,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, 
                 tw->tbeam[slot * kChunkBeams + k] = j;
                 todo = false;
             }
-            if (lane == 0) { TileChunk tc; tc.x0 = ox; tc.y0 = oy; tc.count = __popc(mm); tc.pad = 0; tw->chunk[slot] = tc; }
+            if (lane == 0) { TileChunk tc; tc.x0 = ox; tc.y0 = oy; tc.count = __popc(mm); tc.pad = 0; tw->chunk[slot] = tc; s_cnt2[slot] = tc.count; }
         }
         const unsigned wm = __ballot_sync(0xffffffffu, todo);
         if (wm) {
@@ -259,12 +262,21 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, 
         }
     }
     __syncthreads();
-    if (t == 0) {
-        // the score kernel walks the non-empty windows only
-        int m = 0;
-        for (int sl = 0; sl < 2 * n_groups; sl++)
-            if (tw->chunk[sl].count > 0) tw->order[m++] = sl;
-        tw->n_chunks = m; wk->nf = s_nwide; wk->ns = s_nslow;
+    // the score kernel walks the non-empty windows only: compact their slots (beam order kept)
+    if (warp == 0) {
+        int base_m = 0;
+        for (int s0 = 0; s0 < 2 * n_groups; s0 += 32) {
+            const int sl = s0 + lane;
+            const bool ne = sl < 2 * n_groups && s_cnt2[sl] > 0;
+            const unsigned bm = __ballot_sync(0xffffffffu, ne);
+            if (ne) tw->order[base_m + __popc(bm & ((1u << lane) - 1))] = sl;
+            base_m += __popc(bm);
+        }
+        if (lane == 0) {
+            tw->n_chunks = base_m; wk->nf = s_nwide; wk->ns = s_nslow;
+            // consumed: reset the cloud bounds for the next frame's k_motion
+            for (int c = 0; c < 3; c++) { tw->bounds[2 * c] = 0x7fffffff; tw->bounds[2 * c + 1] = (int)0x80000000; }
+        }
     }
 }
 
@@ -478,7 +490,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
     }
 }
 
-// fit[p] = sum of n_rows partial rows; per-1024-particle min / max-key partials
+// fit[p] = sum of n_rows partial rows; per-256-particle min / max-key partials
 __global__ void __launch_bounds__(256)
 k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gidx0, int *__restrict__ fit,
                      int *__restrict__ blk_min, long long *__restrict__ blk_maxkey)
@@ -487,15 +499,14 @@ k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gid
     __shared__ long long smax[8];
     int mn = 0x7fffffff;
     long long mk = (long long)0x8000000000000000ull;
-    for (int k = 0; k < 4; k++) {
-        const int p = blockIdx.x * kTile + k * 256 + threadIdx.x;
+    {
+        const int p = blockIdx.x * 256 + threadIdx.x;
         if (p < n) {
             int s = 0;
             for (int r = 0; r < n_rows; r++) s += partial[(size_t)r * n + p];
             fit[p] = s;
-            mn = min(mn, s);
-            long long t = extrema_key(s, gidx0 + p);
-            mk = t > mk ? t : mk;
+            mn = s;
+            mk = extrema_key(s, gidx0 + p);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -544,12 +555,17 @@ static int score_tiled_setup()
 static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGeom g, const float *x, const float *y,
                               const float *th, int n, int gidx0, const StepParams *scan, const float *angle, int n_beams,
                               int *fit, int *blk_min, long long *blk_maxkey, Extrema *ext_local,
-                              ScoreFilteredWork *wk, TiledWork *tw, int *partial, int *counters, cudaStream_t stream,
+                              ScoreFilteredWork *wk, TiledWork *tw, const double2 *angle_cs, bool bounds_valid,
+                              int *partial, int *counters, cudaStream_t stream,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
-    k_bounds_reset<<<1, 32, 0, stream>>>(tw);
-    k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw);
-    k_tile_prep<<<1, 1024, 0, stream>>>(scan, angle, n_beams, g, wk, tw);
+    int nl = 6;
+    if (!bounds_valid) {   // poses were not produced by k_motion this frame (test hooks): recompute
+        k_bounds_reset<<<1, 32, 0, stream>>>(tw);
+        k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw);
+        nl += 2;
+    }
+    k_tile_prep<<<1, 1024, 0, stream>>>(scan, angle, angle_cs, n_beams, g, wk, tw);
     dim3 gt((n + kTiledGroup - 1) / kTiledGroup, kTiledY);
     if (ev0) cudaEventRecord(ev0, stream);
     k_score_tiled<<<gt, kTiledThreads, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
@@ -559,11 +575,11 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                                                   partial + (size_t)kTiledY * n, counters);
     k_score_slow<<<(n + 255) / 256, 256, 0, stream>>>(grid, g, x, y, th, n, scan, angle, wk,
                                                       partial + (size_t)(kTiledY + kFastSlices) * n);
-    const int nblk = (n + kTile - 1) / kTile;
+    const int nblk = (n + 255) / 256;
     k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey);
     k_extrema<<<1, 1024, 0, stream>>>(blk_min, blk_maxkey, nblk, x, y, th, gidx0, ext_local);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return 8;
+    return nl;
 }
 
 }  // namespace pf

@@ -66,6 +66,8 @@ struct pfslam_engine {
     ScoreFilteredWork *fwork = nullptr;
     int *score_partial = nullptr;
     TiledWork *twork = nullptr;
+    double2 *angle_cs = nullptr;
+    bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
     // pinned host staging
@@ -158,7 +160,7 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->tiles_local);
     if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
-    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->sp);
+    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->angle_cs); cudaFree(e->sp);
     cudaFreeHost(e->h_sp);
     for (auto ev : e->lap_ev) if (ev) cudaEventDestroy(ev);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
@@ -226,7 +228,10 @@ static int engine_alloc(pfslam_engine *e)
     CUDA_TRY(cudaMemsetAsync(e->fwork, 0, sizeof(ScoreFilteredWork), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->tiles_local, 0, sizeof(float) * e->tiles_block, e->stream));
     k_init_beams<<<ceil_div(e->cfg.n_beams + 32, 128), 128, 0, e->stream>>>(e->angle, e->cfg.n_beams + 32);
-    e->launches++;
+    CUDA_TRY(cudaMalloc(&e->angle_cs, sizeof(double2) * (e->cfg.n_beams + 32)));
+    k_init_beam_trig<<<ceil_div(e->cfg.n_beams + 32, 128), 128, 0, e->stream>>>(e->angle, e->cfg.n_beams + 32, e->angle_cs);
+    k_bounds_reset<<<1, 32, 0, e->stream>>>(e->twork);
+    e->launches += 3;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PFSLAM_OK;
@@ -328,7 +333,8 @@ int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
-    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0);
+    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds);
+    e->bounds_valid = true;
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     if (e->n_ranks == 1) {
@@ -358,7 +364,8 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     } else if (e->score_mode == PFSLAM_SCORE_TILED) {
         int nl = score_tiled_launch(e->tmap, e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                     e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
-                                    e->twork, e->score_partial, e->counters, e->stream, ev0, ev1);
+                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, e->stream, ev0, ev1);
+        e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
         e->launches += nl;
@@ -461,8 +468,7 @@ static int launch_map(pfslam_engine *e)
                                                       e->counters);
     k_map_wall<<<ceil_div(e->cfg.n_beams, 128), 128, 0, e->stream>>>(e->grid, e->geom, e->res, scan, e->angle,
                                                                      e->cfg.n_beams, e->wall_bits, e->counters);
-    k_finish_counters<<<1, 1, 0, e->stream>>>(e->res, e->counters);
-    e->launches += 3;
+    e->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
 }
@@ -649,6 +655,7 @@ int pfslam_get_particles(pfslam_engine *e, float *x, float *y, float *theta, flo
 int pfslam_set_particles(pfslam_engine *e, const float *x, const float *y, const float *theta, const float *w)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->bounds_valid = false;
     CUDA_TRY(cudaSetDevice(e->cfg.device));
     const size_t b = sizeof(float) * e->n;
     if (x) CUDA_TRY(cudaMemcpyAsync(e->x, x, b, cudaMemcpyHostToDevice, e->stream));
