@@ -27,6 +27,7 @@ struct FrameResult {
     int   fit_min, fit_max, best_index;
     float sum_w, sum_w2, neff;
     int   resampled, n_free, n_wall, n_slow;
+    int   kd_size, kd_ins;
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
@@ -314,7 +315,7 @@ k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__re
 __global__ void __launch_bounds__(1024)
 k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restrict__ tiles_all,
          int n_tiles_local, long long tiles_block_floats, int n_global,
-         float *__restrict__ prefix, FrameResult *__restrict__ res)
+         float *__restrict__ prefix, FrameResult *__restrict__ res, int write_pose)
 {
     extern __shared__ float s_t[];            // 2 * n_tiles_global
     const int nt = n_ranks * n_tiles_local;
@@ -336,7 +337,7 @@ k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restri
         float neff = __fdiv_rn(__fmul_rn(p, p), p2);
         int gmin, gmax, best; float pose[3];
         reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
-        res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2];
+        if (write_pose) { res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2]; }
         res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
         res->sum_w = p; res->sum_w2 = p2; res->neff = neff;
         res->resampled = ((double)neff < 0.7 * (double)n_global) ? 1 : 0;

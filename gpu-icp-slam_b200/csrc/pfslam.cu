@@ -18,6 +18,9 @@
 #include "pf_kernels2d.cuh"
 #include "pf_score_filtered.cuh"
 #include "pf_score_tiled.cuh"
+#include "pf_kernels_kd.cuh"
+
+#include <algorithm>
 
 using namespace pf;
 
@@ -74,6 +77,14 @@ struct pfslam_engine {
     float *h_scan = nullptr;
     FrameResult *h_res = nullptr;
     long long launches = 0;
+    // kd-tree point-cloud path
+    KdNode *kd = nullptr; int kd_cap = 0;
+    KdState *ks = nullptr;
+    int *bits_blk = nullptr; int n_bits_blk = 0;
+    int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 4096;
+    float2 *kd_pts = nullptr; int *kd_nn_idx = nullptr, *kd_ins_index = nullptr;
+    bool kd_empty = true;                  // no tree yet (kdSize == 0, kernel.cu:1714)
+    std::vector<KdNode> h_kd;
     // per-step parameters (device copy + pinned ring) and the captured step graph
     StepParams *sp = nullptr;
     StepParams *h_sp = nullptr;            // kParamSlots pinned slots
@@ -161,6 +172,8 @@ int pfslam_destroy(pfslam_engine *e)
     if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
     cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->angle_cs); cudaFree(e->sp);
+    cudaFree(e->kd); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
+    cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index);
     cudaFreeHost(e->h_sp);
     for (auto ev : e->lap_ev) if (ev) cudaEventDestroy(ev);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
@@ -212,6 +225,19 @@ static int engine_alloc(pfslam_engine *e)
     CUDA_TRY(cudaMemsetAsync(e->sp, 0, sizeof(StepParams), e->stream));
     CUDA_TRY(cudaMallocHost(&e->h_sp, sizeof(StepParams) * kParamSlots));
     for (auto &ev : e->lap_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (e->cfg.path == PFSLAM_PATH_KD) {
+        e->kd_cap = e->cfg.kd_capacity > 0 ? e->cfg.kd_capacity : (1 << 21);
+        CUDA_TRY(cudaMalloc(&e->kd, sizeof(KdNode) * (size_t)e->kd_cap));
+        CUDA_TRY(cudaMalloc(&e->ks, sizeof(KdState)));
+        CUDA_TRY(cudaMemsetAsync(e->ks, 0, sizeof(KdState), e->stream));
+        e->n_bits_blk = ceil_div((int)(e->bits_bytes / 4), kBitsBlockWords);
+        CUDA_TRY(cudaMalloc(&e->bits_blk, sizeof(int) * 2 * e->n_bits_blk));
+        CUDA_TRY(cudaMalloc(&e->free_cells, sizeof(int) * e->pc_cap));
+        CUDA_TRY(cudaMalloc(&e->wall_cells, sizeof(int) * e->pc_cap));
+        CUDA_TRY(cudaMalloc(&e->kd_pts, sizeof(float2) * 2 * e->pc_cap));
+        CUDA_TRY(cudaMalloc(&e->kd_nn_idx, sizeof(int) * 2 * e->pc_cap));
+        CUDA_TRY(cudaMalloc(&e->kd_ins_index, sizeof(int) * e->pc_cap));
+    }
     CUDA_TRY(cudaMallocHost(&e->h_scan, sizeof(float) * e->cfg.n_beams));
     CUDA_TRY(cudaMallocHost(&e->h_res, sizeof(FrameResult)));
     // initial state: kernel.cu:122-132
@@ -252,8 +278,10 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     if (cfg->n_ranks > 1 && (cfg->n_particles % kTile != 0 || cfg->particle_offset % kTile != 0 ||
                              (long long)cfg->n_particles * cfg->n_ranks != cfg->n_particles_global))
         return set_error(PFSLAM_ERR_ARG, "sharded engines need n_particles %% 1024 == 0 and equal shards");
-    if (cfg->path != PFSLAM_PATH_GRID2D)
-        return set_error(PFSLAM_ERR_UNSUPPORTED, "path %d not built yet (2D occupancy grid only)", cfg->path);
+    if (cfg->path != PFSLAM_PATH_GRID2D && cfg->path != PFSLAM_PATH_KD)
+        return set_error(PFSLAM_ERR_ARG, "unknown path %d", cfg->path);
+    if (cfg->path == PFSLAM_PATH_KD && cfg->n_ranks != 1)
+        return set_error(PFSLAM_ERR_UNSUPPORTED, "the kd path is single-GPU in this build");
     if (cfg->score_mode < PFSLAM_SCORE_EXACT || cfg->score_mode > PFSLAM_SCORE_TILED)
         return set_error(PFSLAM_ERR_ARG, "bad score_mode");
     int ndev = 0;
@@ -453,7 +481,8 @@ static int launch_prefix(pfslam_engine *e)
 {
     const int nt = e->n_tiles * e->n_ranks;
     k_prefix<<<1, 1024, sizeof(float) * 2 * nt, e->stream>>>(e->ext_all, e->n_ranks, e->tiles_all, e->n_tiles,
-                                                             e->tiles_block, e->n_global, e->prefix, e->res);
+                                                             e->tiles_block, e->n_global, e->prefix, e->res,
+                                                             e->cfg.path == PFSLAM_PATH_KD ? 0 : 1);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
@@ -496,6 +525,122 @@ int pfslam_phase_resample(pfslam_engine *e, int32_t frame)
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// kd-tree path, host side.  Tree (re)builds run on the host like the reference's KDTree::Create /
+// Balance (kdtree.cpp:25-67): the shape depends on std::sort's order among equal keys, and calling the
+// same std::sort on the same sequence is what keeps it identical to the reference build.
+struct KdPt { float x, y, z, w; };
+static bool kd_less_x(const KdPt &a, const KdPt &b) { return a.x < b.x; }
+static bool kd_less_y(const KdPt &a, const KdPt &b) { return a.y < b.y; }
+static bool kd_less_z(const KdPt &a, const KdPt &b) { return a.z < b.z; }
+
+static void kd_build_range(KdPt *first, KdPt *last, KdNode *list, int idx, int parent)
+{
+    const int axis = parent < 0 ? 0 : (list[parent].axis + 1) % 3;
+    std::sort(first, last, axis == 0 ? kd_less_x : axis == 1 ? kd_less_y : kd_less_z);
+    const int size = (int)(last - first), mid = size / 2;
+    KdNode &n = list[idx];
+    n.axis = axis; n.left = -1; n.right = -1; n.parent = parent;
+    n.x = first[mid].x; n.y = first[mid].y; n.z = first[mid].z; n.w = first[mid].w;
+    if (mid > 0) { n.left = idx + 1; kd_build_range(first, first + mid, list, idx + 1, idx); }
+    if (mid < size - 1) { list[idx].right = idx + mid + 1; kd_build_range(first + mid + 1, last, list, idx + mid + 1, idx); }
+}
+
+static void kd_build(std::vector<KdPt> &pts, KdNode *list)
+{
+    if (pts.empty()) return;
+    std::sort(pts.begin(), pts.end(), kd_less_x);          // Create sorts by x, then InsertList sorts again
+    kd_build_range(pts.data(), pts.data() + pts.size(), list, 0, -1);
+}
+
+// frame % 100 == 5 (kernel.cu:1707-1711): device tree -> host rebuild -> device
+static int kd_balance(pfslam_engine *e)
+{
+    KdState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, e->ks, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (st.size <= 0) return PFSLAM_OK;
+    e->h_kd.resize(st.size);
+    CUDA_TRY(cudaMemcpyAsync(e->h_kd.data(), e->kd, sizeof(KdNode) * st.size, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    std::vector<KdPt> pts(st.size);
+    for (int i = 0; i < st.size; i++) { pts[i].x = e->h_kd[i].x; pts[i].y = e->h_kd[i].y; pts[i].z = e->h_kd[i].z; pts[i].w = e->h_kd[i].w; }
+    kd_build(pts, e->h_kd.data());
+    CUDA_TRY(cudaMemcpyAsync(e->kd, e->h_kd.data(), sizeof(KdNode) * st.size, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+// PFUpdateMapKD (kernel.cu:1406-1540)
+static int kd_update_map(pfslam_engine *e)
+{
+    const int n_words = (int)(e->bits_bytes / 4);
+    CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, e->stream));
+    k_kd_mark<<<e->cfg.n_beams, 128, 0, e->stream>>>(e->geom, e->res, e->sp, e->angle, e->free_bits, e->wall_bits);
+    k_bits_count<<<e->n_bits_blk, 256, 0, e->stream>>>(e->free_bits, e->wall_bits, n_words, e->bits_blk);
+    k_bits_offsets<<<1, 32, 0, e->stream>>>(e->bits_blk, e->n_bits_blk, e->ks);
+    k_bits_scatter<<<e->n_bits_blk, 256, 0, e->stream>>>(e->free_bits, e->wall_bits, n_words, e->bits_blk,
+                                                         e->free_cells, e->wall_cells, e->pc_cap);
+    k_kd_points_nn<<<ceil_div(2 * e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->res, e->ks, e->wall_cells,
+                                                                       e->free_cells, e->pc_cap, e->kd_pts, e->kd_nn_idx);
+    e->launches += 5;
+    if (e->kd_empty) {
+        // first scan: build the tree from the wall points on the host (kernel.cu:1532-1536)
+        KdState st;
+        CUDA_TRY(cudaMemcpyAsync(&st, e->ks, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        const int nW = std::min(std::min(st.n_wall, e->pc_cap), e->kd_cap);
+        if (nW > 0) {
+            std::vector<float2> p(nW);
+            CUDA_TRY(cudaMemcpy(p.data(), e->kd_pts, sizeof(float2) * nW, cudaMemcpyDeviceToHost));
+            std::vector<KdPt> pts(nW);
+            for (int i = 0; i < nW; i++) { pts[i].x = p[i].x; pts[i].y = p[i].y; pts[i].z = 0.0f; pts[i].w = 0.0f; }   // Q12: w = 0
+            e->h_kd.assign(nW, KdNode());
+            kd_build(pts, e->h_kd.data());
+            CUDA_TRY(cudaMemcpy(e->kd, e->h_kd.data(), sizeof(KdNode) * nW, cudaMemcpyHostToDevice));
+            st.size = nW; st.n_ins = nW;
+            CUDA_TRY(cudaMemcpy(e->ks, &st, sizeof st, cudaMemcpyHostToDevice));
+            e->kd_empty = false;
+        }
+    } else {
+        k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 0, e->kd_pts, e->kd_nn_idx);
+        k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 1, e->kd_pts, e->kd_nn_idx);
+        k_kd_insert<<<1, 1024, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, e->kd_cap, e->kd_pts, e->kd_nn_idx, e->kd_ins_index);
+        e->launches += 3;
+    }
+    k_kd_finish<<<1, 1, 0, e->stream>>>(e->res, e->ks, e->counters);
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+// particleFilter, kd variant (kernel.cu:1702-1761)
+static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
+{
+    int rc = push_params(e, scan_dev ? scan_dev : e->scan, frame);
+    if (rc) return rc;
+    if (frame % 100 == 5 && !e->kd_empty && (rc = kd_balance(e))) return rc;
+    if (e->kd_empty) {
+        CUDA_TRY(cudaMemsetAsync(e->res, 0, sizeof(FrameResult), e->stream));      // robotPos = 0 (kernel.cu:1715)
+        return kd_update_map(e);
+    }
+    if ((rc = pfslam_phase_motion(e, frame))) return rc;
+    k_score_kd<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
+                                                         e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+    k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y, e->th, e->gidx0, e->ext_local);
+    e->launches += 2;
+    e->bounds_valid = false;
+    if ((rc = pfslam_phase_weights(e))) return rc;
+    k_icp<<<1, 1024, sizeof(float) * 5 * e->cfg.n_beams, e->stream>>>(e->kd, e->ext_all, e->n_ranks, e->sp, e->angle,
+                                                                    e->cfg.n_beams, e->res);
+    e->launches += 1;
+    if ((rc = launch_prefix(e))) return rc;
+    if ((rc = kd_update_map(e))) return rc;
+    return pfslam_phase_resample(e, frame);
 }
 
 static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
@@ -552,6 +697,7 @@ int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
     if (e->n_ranks != 1)
         return set_error(PFSLAM_ERR_STATE, "sharded engines are stepped phase by phase by the multi-GPU host");
     CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (e->cfg.path == PFSLAM_PATH_KD) return kd_step(e, scan_dev, frame);
     const float *scan = scan_dev ? scan_dev : e->scan;
     if (e->use_graph && !e->prof_on && !e->graph_failed) {
         if (!e->graph_exec && build_graph(e) != 0) e->graph_failed = true;
@@ -581,6 +727,7 @@ static void copy_result(const FrameResult *r, pfslam_frame_result *out)
     out->sum_w = r->sum_w; out->sum_w2 = r->sum_w2; out->neff = r->neff;
     out->resampled = r->resampled; out->n_free_cells = r->n_free; out->n_wall_cells = r->n_wall;
     out->n_slow_evals = r->n_slow;
+    out->kd_size = r->kd_size; out->kd_inserted = r->kd_ins;
 }
 
 int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
@@ -633,7 +780,13 @@ int pfslam_score_particles(pfslam_engine *e, const float *scan_host, int32_t *fi
     if (!e || !scan_host || !fit_out) return set_error(PFSLAM_ERR_ARG, "null argument");
     int rc = pfslam_upload_scan(e, scan_host);
     if (rc) return rc;
-    if ((rc = pfslam_phase_score(e, nullptr))) return rc;
+    if (e->cfg.path == PFSLAM_PATH_KD) {
+        if (e->kd_empty) return set_error(PFSLAM_ERR_STATE, "no kd tree yet");
+        if ((rc = push_params(e, e->scan, e->cur.frame))) return rc;
+        k_score_kd<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
+                                                             e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+        e->launches++;
+    } else if ((rc = pfslam_phase_score(e, nullptr))) return rc;
     CUDA_TRY(cudaMemcpyAsync(fit_out, e->fit, sizeof(int) * e->n, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PFSLAM_OK;
@@ -714,6 +867,53 @@ int pfslam_device_buffer(pfslam_engine *e, int32_t which, void **dev_ptr, int64_
     case PFSLAM_BUF_SCAN: *dev_ptr = e->scan; *bytes = 4ll * e->cfg.n_beams; break;
     default: return set_error(PFSLAM_ERR_ARG, "unknown buffer %d", which);
     }
+    return PFSLAM_OK;
+}
+
+int pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_out)
+{
+    if (!e || !q_xyz || !idx_out || n <= 0) return set_error(PFSLAM_ERR_ARG, "bad argument");
+    if (e->cfg.path != PFSLAM_PATH_KD) return set_error(PFSLAM_ERR_STATE, "engine was not created with PFSLAM_PATH_KD");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    float *dq = nullptr; int *di = nullptr;
+    CUDA_TRY(cudaMalloc(&dq, sizeof(float) * 3 * n));
+    cudaError_t ce = cudaMalloc(&di, sizeof(int) * n);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(dq, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) { k_kd_nn<<<ceil_div(n, 128), 128, 0, e->stream>>>(e->kd, e->ks, dq, n, di); e->launches++; ce = cudaGetLastError(); }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(idx_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(dq); cudaFree(di);
+    if (ce != cudaSuccess) return set_error(PFSLAM_ERR_CUDA, "kd_nn: %s", cudaGetErrorString(ce));
+    return PFSLAM_OK;
+}
+
+int pfslam_get_kd(pfslam_engine *e, void *nodes_out, int32_t cap, int32_t *n_nodes)
+{
+    if (!e || !n_nodes) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (e->cfg.path != PFSLAM_PATH_KD) { *n_nodes = 0; return PFSLAM_OK; }
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    KdState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, e->ks, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    *n_nodes = st.size;
+    if (nodes_out && cap > 0 && st.size > 0) {
+        CUDA_TRY(cudaMemcpyAsync(nodes_out, e->kd, sizeof(KdNode) * (size_t)std::min(cap, st.size), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return PFSLAM_OK;
+}
+
+int pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes)
+{
+    if (!e || !nodes_in || n_nodes <= 0) return set_error(PFSLAM_ERR_ARG, "bad argument");
+    if (e->cfg.path != PFSLAM_PATH_KD) return set_error(PFSLAM_ERR_STATE, "engine was not created with PFSLAM_PATH_KD");
+    if (n_nodes > e->kd_cap) return set_error(PFSLAM_ERR_ARG, "tree larger than kd_capacity");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    KdState st; memset(&st, 0, sizeof st); st.size = n_nodes;
+    CUDA_TRY(cudaMemcpyAsync(e->kd, nodes_in, sizeof(KdNode) * (size_t)n_nodes, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->ks, &st, sizeof st, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->kd_empty = false;
     return PFSLAM_OK;
 }
 

@@ -38,6 +38,7 @@ class Config(C.Structure):
         ("map_scale_x", C.c_float), ("map_scale_y", C.c_float),
         ("map_res_x", C.c_float), ("map_res_y", C.c_float),
         ("device", C.c_int32), ("path", C.c_int32), ("score_mode", C.c_int32), ("quirks", C.c_uint32),
+        ("kd_capacity", C.c_int32),
     ]
 
 
@@ -47,7 +48,7 @@ class FrameResult(C.Structure):
         ("pose", C.c_float * 3), ("fit_min", C.c_int32), ("fit_max", C.c_int32),
         ("best_index", C.c_int32), ("sum_w", C.c_float), ("sum_w2", C.c_float), ("neff", C.c_float),
         ("resampled", C.c_int32), ("n_free_cells", C.c_int32), ("n_wall_cells", C.c_int32),
-        ("n_slow_evals", C.c_int32),
+        ("n_slow_evals", C.c_int32), ("kd_size", C.c_int32), ("kd_inserted", C.c_int32),
     ]
 
     def as_dict(self):
@@ -88,6 +89,9 @@ _SIGS = {
     "pfslam_get_pose": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pfslam_synchronize": (C.c_int, [C.c_void_p]),
     "pfslam_device_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "pfslam_kd_nn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pfslam_get_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "pfslam_set_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "pfslam_launch_count": (C.c_int64, [C.c_void_p]),
     "pfslam_profile_score": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pfslam_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -188,7 +192,7 @@ class ParticleFilter:
 
     def __init__(self, n_particles=1000, scene=None, n_beams=1081, device=0,
                  score_mode=SCORE_TILED, quirks=QUIRKS_REFERENCE, path=PATH_GRID2D,
-                 n_particles_global=None, particle_offset=0, n_ranks=1):
+                 n_particles_global=None, particle_offset=0, n_ranks=1, kd_capacity=0):
         self._lib = load_library()
         self._h = C.c_void_p()
         scene = scene or Scene()
@@ -206,6 +210,7 @@ class ParticleFilter:
         cfg.path = int(path)
         cfg.score_mode = int(score_mode)
         cfg.quirks = int(quirks)
+        cfg.kd_capacity = int(kd_capacity)
         self.cfg = cfg
         self.n = cfg.n_particles
         self.n_beams = cfg.n_beams
@@ -335,6 +340,27 @@ class ParticleFilter:
         self._check(self._lib.pfslam_get_pose(self._h, p))
         return [float(v) for v in p]
 
+    # -- kd-tree path ---------------------------------------------------------------------------
+    def kd_nn(self, q_xyz):
+        """findCorrespondenceIndexKD alone (src/kernel.cu:924): node index of each (x, y, z) query."""
+        q = np.ascontiguousarray(q_xyz, dtype=np.float32).reshape(-1, 3)
+        out = np.empty(q.shape[0], dtype=np.int32)
+        self._check(self._lib.pfslam_kd_nn(self._h, q.ctypes.data, q.shape[0], out.ctypes.data))
+        return out
+
+    def get_kd(self):
+        """the tree as int32[n, 8] words in the reference's KDTree::Node layout"""
+        n = C.c_int32()
+        self._check(self._lib.pfslam_get_kd(self._h, None, 0, C.byref(n)))
+        nodes = np.zeros((max(n.value, 1), 8), dtype=np.int32)
+        if n.value:
+            self._check(self._lib.pfslam_get_kd(self._h, nodes.ctypes.data, n.value, C.byref(n)))
+        return nodes[: n.value]
+
+    def set_kd(self, nodes):
+        a = np.ascontiguousarray(nodes, dtype=np.int32).reshape(-1, 8)
+        self._check(self._lib.pfslam_set_kd(self._h, a.ctypes.data, a.shape[0]))
+
     def device_buffer(self, which):
         ptr, nbytes = C.c_void_p(), C.c_int64()
         self._check(self._lib.pfslam_device_buffer(self._h, int(which), C.byref(ptr), C.byref(nbytes)))
@@ -385,4 +411,6 @@ def getPCData():
     if _engine is None:
         raise PfslamError("getPCData before particleFilterInit")
     x, y, th, w = _engine.get_particles()
-    return np.stack([x, y, th, w], axis=1), _engine.get_grid(), None, _engine.n, 0, list(_robot_pos)
+    kd = _engine.get_kd() if _engine.cfg.path == PATH_KD else None
+    return (np.stack([x, y, th, w], axis=1), _engine.get_grid(), kd, _engine.n,
+            0 if kd is None else len(kd), list(_robot_pos))

@@ -58,6 +58,7 @@ typedef struct pfslam_config {
     int32_t  path;               /* PFSLAM_PATH_* */
     int32_t  score_mode;         /* PFSLAM_SCORE_* */
     uint32_t quirks;             /* PFSLAM_QUIRK_* bit set */
+    int32_t  kd_capacity;        /* kd path: node capacity (KD_MAX_SIZE, kernel.cu:77); 0 = 2 097 152 */
 } pfslam_config;
 
 /* Per-frame results, the engine-side equivalent of robotPos + the timers' inputs
@@ -71,6 +72,8 @@ typedef struct pfslam_frame_result {
     int32_t n_free_cells;        /* cells cleared / reinforced by the map update this frame */
     int32_t n_wall_cells;
     int32_t n_slow_evals;        /* (particle, beam) pairs the filtered scorer re-did exactly */
+    int32_t kd_size;             /* kd path: nodes in the tree after this frame (kdSize, kernel.cu:80) */
+    int32_t kd_inserted;         /* kd path: nodes inserted this frame */
 } pfslam_frame_result;
 
 /* ---- life cycle: particleFilterInit(Scene*) / particleFilterFree(), kernel.cu:107-178 ---- */
@@ -116,6 +119,15 @@ int  pfslam_set_grid(pfslam_engine *e, const int8_t *grid_in);
 int  pfslam_get_map_dim(pfslam_engine *e, int32_t *map_w, int32_t *map_h);
 int  pfslam_get_pose(pfslam_engine *e, float pose[3]);
 int  pfslam_synchronize(pfslam_engine *e);
+
+/* ---- kd-tree point-cloud path (PFSLAM_PATH_KD) ----
+ * nodes use the reference's KDTree::Node layout (kdtree.hpp:16-27): 8 x 4 B
+ * {int axis, left, right, parent; float x, y, z, w}. */
+/* kd-tree NN lookup alone (findCorrespondenceIndexKD, kernel.cu:924): n queries (x,y,z) -> node index */
+int  pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_out);
+/* getPCData's kd part (kernel.cu:810-811): copies up to cap nodes, returns the tree size */
+int  pfslam_get_kd(pfslam_engine *e, void *nodes_out, int32_t cap, int32_t *n_nodes);
+int  pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes);
 
 /* ---- device buffers a multi-GPU host all-gathers between phases (device pointers, engine-owned) ---- */
 #define PFSLAM_BUF_EXTREMA_LOCAL 0  /* 8 x 4 B: {min, max, argmax global idx, x, y, theta, 0, 0}   */

@@ -23,6 +23,12 @@ int EvaluateParticle(MAP_TYPE *map, glm::ivec2 map_dim, Patch map_params, Partic
                      glm::vec3 pos, float *lidar);                               /* kernel.cu:257 */
 void ParticleAddNoise(Particle &particle, int frame, int idx);                   /* kernel.cu:375 */
 
+/* the reference's 3x3 SVD (src/svd3.h:354, a non-inline function compiled into kernel.o) */
+void svd(float a11, float a12, float a13, float a21, float a22, float a23, float a31, float a32, float a33,
+         float &u11, float &u12, float &u13, float &u21, float &u22, float &u23, float &u31, float &u32, float &u33,
+         float &s11, float &s12, float &s13, float &s21, float &s22, float &s23, float &s31, float &s32, float &s33,
+         float &v11, float &v12, float &v13, float &v21, float &v22, float &v23, float &v31, float &v32, float &v33);
+
 Lidar::Lidar(std::string) {}
 Lidar::~Lidar() {}
 
@@ -93,5 +99,22 @@ void ref_kd_insert(const float *pt4, void *nodes, int size)
     KDTree::InsertNode(glm::vec4(pt4[0], pt4[1], pt4[2], pt4[3]), (KDTree::Node *)nodes, size);
 }
 void ref_kd_balance(void *nodes, int size) { KDTree::Balance((KDTree::Node *)nodes, size); }
+
+/* Rotation the reference derives from the ICP cross-covariance (kernel.cu:1056-1079): feeds W to the
+ * reference's svd() with the reference's argument order and returns R = U V^T (glm column-major, 9
+ * floats) so the oracle's closed form can be compared against it. */
+void ref_icp_rotation(const float *w9, float *r9)
+{
+    glm::mat3 W, U, S, V;
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) W[c][r] = w9[3 * c + r];
+    svd(W[0][0], W[0][1], W[0][2], W[1][0], W[1][1], W[1][2], W[2][0], W[2][1], W[2][2],
+        U[0][0], U[0][1], U[0][2], U[1][0], U[1][1], U[1][2], U[2][0], U[2][1], U[2][2],
+        S[0][0], S[0][1], S[0][2], S[1][0], S[1][1], S[1][2], S[2][0], S[2][1], S[2][2],
+        V[0][0], V[0][1], V[0][2], V[1][0], V[1][1], V[1][2], V[2][0], V[2][1], V[2][2]);
+    glm::mat3 Um(glm::vec3(U[0][0], U[1][0], U[2][0]), glm::vec3(U[0][1], U[1][1], U[2][1]), glm::vec3(U[0][2], U[1][2], U[2][2]));
+    glm::mat3 Vt(glm::vec3(V[0][0], V[0][1], V[0][2]), glm::vec3(V[1][0], V[1][1], V[1][2]), glm::vec3(V[2][0], V[2][1], V[2][2]));
+    glm::mat3 R = Um * Vt;
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) r9[3 * c + r] = R[c][r];
+}
 
 }

@@ -42,7 +42,7 @@ def ocfg(trig=TRIG_CUDA, mad=MAD_FUSED, q1=1, n_beams=1081, scale=40.0, res=0.02
 
 
 def build_oracle():
-    src = [os.path.join(ORACLE_DIR, f) for f in ("pfo.c", "pfo_kd.c", "pfo.h")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("pfo.c", "pfo_kd.cpp", "pfo.h")]
     if os.path.exists(ORACLE_SO) and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(s) for s in src):
         return
     subprocess.run(["make", "-C", ORACLE_DIR, "_build/liboracle.so"], check=True, stdout=subprocess.DEVNULL)
@@ -194,4 +194,70 @@ class OracleFilter:
     def step(self, scan, frame):
         sc = np.ascontiguousarray(scan, dtype=np.float32)
         self.o.pfo_step2d(self.s, P(sc), int(frame))
+        return self.s.contents
+
+
+# ---- kd path ---------------------------------------------------------------------------------------
+class OKdState(C.Structure):
+    _fields_ = [("cfg", OCfg), ("n", C.c_int), ("x", fp), ("y", fp), ("th", fp), ("w", fp), ("weff", fp),
+                ("fit", ip), ("cdf", fp), ("tree", C.c_void_p), ("kd_size", C.c_int), ("kd_cap", C.c_int),
+                ("free_mask", ubp), ("wall_mask", ubp), ("robot", C.c_float * 3),
+                ("fit_min", C.c_int32), ("fit_max", C.c_int32), ("best", C.c_int),
+                ("sum_w", C.c_float), ("sum_w2", C.c_float), ("neff", C.c_float), ("resampled", C.c_int),
+                ("n_free_pts", C.c_int), ("n_wall_pts", C.c_int), ("n_inserted", C.c_int)]
+
+
+def load_oracle_kd():
+    o = load_oracle()
+    if getattr(o, "_kd_typed", False):
+        return o
+    o.pfo_kd_create.argtypes = [fp, C.c_int, C.c_void_p]
+    o.pfo_kd_insert.argtypes = [fp, C.c_void_p, C.c_int]
+    o.pfo_kd_balance.argtypes = [C.c_void_p, C.c_int]
+    o.pfo_kd_nn.restype = C.c_int
+    o.pfo_kd_nn.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+    o.pfo_kd_score.restype = C.c_int
+    o.pfo_kd_score.argtypes = [C.POINTER(OCfg), C.c_void_p, C.c_float, C.c_float, C.c_float, fp]
+    o.pfo_asinf.restype = C.c_float
+    o.pfo_asinf.argtypes = [C.c_float]
+    o.pfo_kd_icp.argtypes = [C.POINTER(OCfg), C.c_void_p, fp, fp, fp, fp]
+    o.pfo_kd_create_state.restype = C.POINTER(OKdState)
+    o.pfo_kd_create_state.argtypes = [C.POINTER(OCfg), C.c_int, C.c_int]
+    o.pfo_kd_destroy_state.argtypes = [C.POINTER(OKdState)]
+    o.pfo_kd_step.argtypes = [C.POINTER(OKdState), fp, C.c_int]
+    o.pfo_kd_update_map.argtypes = [C.POINTER(OKdState), fp]
+    o._kd_typed = True
+    return o
+
+
+class OracleKdFilter:
+    def __init__(self, n, cfg=None, kd_cap=1 << 20):
+        self.o = load_oracle_kd()
+        self.cfg = cfg or ocfg()
+        self.n = n
+        self.s = self.o.pfo_kd_create_state(C.byref(self.cfg), n, kd_cap)
+
+    def close(self):
+        if self.s:
+            self.o.pfo_kd_destroy_state(self.s)
+            self.s = None
+
+    def arr(self, name, count, dtype):
+        return np.ctypeslib.as_array(getattr(self.s.contents, name), shape=(count,)).view(dtype)
+
+    x = property(lambda s: s.arr("x", s.n, np.float32))
+    y = property(lambda s: s.arr("y", s.n, np.float32))
+    th = property(lambda s: s.arr("th", s.n, np.float32))
+    w = property(lambda s: s.arr("w", s.n, np.float32))
+    fit = property(lambda s: s.arr("fit", s.n, np.int32))
+
+    @property
+    def tree(self):
+        n = self.s.contents.kd_size
+        buf = (C.c_int32 * (8 * max(n, 1))).from_address(self.s.contents.tree)
+        return np.ctypeslib.as_array(buf).reshape(-1, 8)[:n]
+
+    def step(self, scan, frame):
+        sc = np.ascontiguousarray(scan, dtype=np.float32)
+        self.o.pfo_kd_step(self.s, P(sc), int(frame))
         return self.s.contents

@@ -216,7 +216,7 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(g.PfslamError):
         g.ParticleFilter(0)
     with pytest.raises(g.PfslamError):
-        g.ParticleFilter(128, path=g.PATH_KD)
+        g.ParticleFilter(128, path=7)
     with pytest.raises(g.PfslamError):
         g.ParticleFilter(128, device=99)
     with g.ParticleFilter(128) as pf:
