@@ -26,15 +26,22 @@ METRIC = "lidar_frames_per_sec_at_65536_particles_per_gpu"
 UNIT = "frames/s"
 
 
-def workload_scans(n_frames):
-    """real train_lidar0 scans (committed 256-frame fixture), played 1..255..1.. (ping-pong keeps the
-    motion physically continuous for any number of steps)"""
+def workload_scans(n_frames, dataset=None):
+    """real train_lidar scans played 1..last..1.. (ping-pong keeps the motion physically continuous
+    for any number of steps): the committed 256-frame train_lidar0 fixture, or a full converted
+    dataset from data/_cache when it travelled to the box"""
     from gpu_icp_slam_b200 import scans as S
-    fx = S.load(os.path.join(ROOT, "tests", "golden", "train_lidar0_first256.scans.u16"))
+    path = os.path.join(ROOT, "tests", "golden", "train_lidar0_first256.scans.u16")
+    if dataset:
+        full = os.path.join(ROOT, "data", "_cache", dataset + ".scans.u16")
+        if os.path.exists(full):
+            path = full
+    fx = S.load(path)
+    last = min(len(fx) - 1, 4000)
     order, f, d = [], 1, 1
     for _ in range(n_frames):
         order.append(f)
-        if f + d > 255 or f + d < 1:
+        if f + d > last or f + d < 1:
             d = -d
         f += d
     return np.ascontiguousarray(fx[order]), order
@@ -210,7 +217,8 @@ def run_ours(args):
 
     n = args.particles
     K, W = args.steps, max(args.warmup, 3)
-    scans, order = workload_scans(K + W + 8)
+    kd = args.path == "kd"
+    scans, order = workload_scans(K + W + 8, "train_lidar3" if kd else None)
     # everything runs on one non-default stream (the legacy default stream cannot be graph-captured)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -219,7 +227,7 @@ def run_ours(args):
         from gpu_icp_slam_b200.dist import ShardedParticleFilter
         pf = ShardedParticleFilter(n, device=local_rank)
     else:
-        pf = g.ParticleFilter(n, device=local_rank)
+        pf = g.ParticleFilter(n, device=local_rank, path=g.PATH_KD if kd else g.PATH_GRID2D)
         pf.set_stream(stream.cuda_stream)
 
     scans_dev = torch.from_numpy(scans).cuda()
@@ -281,7 +289,7 @@ def run_ours(args):
         step_async(W + k)
     ker, n_prof = eng.profile_read()
     eng.profile_enable(False)
-    iso_ms = [eng.profile_score() for _ in range(10)]
+    iso_ms = [eng.profile_score() for _ in range(10)] if not kd else [(0.0, 0.0)]
     r = eng.fetch_result()
 
     # ---- e2e: the public host API, host scan in, host pose out, every step
@@ -305,13 +313,16 @@ def run_ours(args):
         peak, peak_src = peaks()
         scale = world * n / 65536.0                      # 65 536-particle frame equivalents per frame
         alg_bytes = n * (N_BEAMS + 20) + 4 * N_BEAMS     # N*1101 + 4324 per launch (per GPU)
+        if kd:   # one 32-B node per tree level per (particle, beam): N*B*32*ceil(log2 kdSize)
+            alg_bytes = n * N_BEAMS * 32 * int(np.ceil(np.log2(max(r.kd_size, 2))))
         achieved = alg_bytes / (ker * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": K / (dev_ms * 1e-3) * scale, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC + ("_kd" if kd else ""), "value": K / (dev_ms * 1e-3) * scale, "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
             "data": "real train_lidar0 scans (committed 256-frame fixture, ping-pong); the full .mat is not on the GPU box",
-            "config": {"workload": "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, 65 536 particles per GPU",
+            "config": {"workload": ("train_lidar3 (or the train_lidar0 fixture), kd-tree point cloud @ 25 mm, 65 536 particles per GPU" if kd else
+                                    "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, 65 536 particles per GPU"),
                        "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS,
                        "score_mode": "tiled (TMA-staged smem windows, bit-exact)", "l2_flush": "256 MiB memset between timed steps (untimed)",
                        "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
@@ -321,16 +332,16 @@ def run_ours(args):
             "e2e": {"value": K / (e2e_ms * 1e-3) * scale, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * N_BEAMS, "d2h_bytes_per_step": C.sizeof(g.FrameResult)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_score_tiled", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_score_kd" if kd else "k_score_tiled", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker, "kernel_launches_timed": n_prof,
                          "kernel_ms_isolated": float(np.mean([a for a, _ in iso_ms])),
                          "scoring_phase_ms_isolated": float(np.mean([b for _, b in iso_ms]))},
             "clocks": clocks,
             "last_frame": {"neff": r.neff, "resampled": r.resampled, "n_slow_evals": r.n_slow_evals,
-                           "slow_eval_frac": r.n_slow_evals / float(n * N_BEAMS)},
+                           "slow_eval_frac": r.n_slow_evals / float(n * N_BEAMS), "kd_size": r.kd_size},
         }
-        if not args.no_cpu and world == 1:
+        if not args.no_cpu and world == 1 and not kd:
             fps, kind, what = cpu_reference_frames_per_sec(n, max(2, min(8, int(20.0 / (n * N_BEAMS * 35e-9 + 1e-3)))), 1)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": kind, "sample": what}
         print(json.dumps(line), flush=True)
@@ -346,6 +357,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=65536, help="particles per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--path", default="grid2d", choices=["grid2d", "kd"], help="map representation (BASELINE configs 2 / 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

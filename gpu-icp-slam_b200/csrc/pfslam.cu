@@ -629,8 +629,11 @@ static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
         return kd_update_map(e);
     }
     if ((rc = pfslam_phase_motion(e, frame))) return rc;
+    const bool prof = e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2;
+    if (prof) cudaEventRecord(e->prof_ev[2 * e->prof_n], e->stream);
     k_score_kd<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
                                                          e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+    if (prof) { cudaEventRecord(e->prof_ev[2 * e->prof_n + 1], e->stream); e->prof_n++; }
     k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y, e->th, e->gidx0, e->ext_local);
     e->launches += 2;
     e->bounds_valid = false;
