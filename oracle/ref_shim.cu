@@ -32,6 +32,7 @@ void svd(float a11, float a12, float a13, float a21, float a22, float a23, float
 Lidar::Lidar(std::string) {}
 Lidar::~Lidar() {}
 
+#ifndef REF_SHIM_LIDAR_ONLY
 static Patch make_patch(float sx, float sy, float rx, float ry)
 {
     Patch p; p.scale = glm::vec3(sx, sy, 0.0f); p.resolution = glm::vec3(rx, ry, 1.0f);
@@ -118,3 +119,4 @@ void ref_icp_rotation(const float *w9, float *r9)
 }
 
 }
+#endif
