@@ -10,6 +10,7 @@ namespace pf {
 
 constexpr int kTile = 1024;            // reduction / scan tile (pfslam order)
 constexpr int kScanThreads = 256;      // 8 warps x 32 lanes x 4 items
+constexpr int kFusedPrefixMaxTiles = 1024;   // k_weights_scan folds the prefix step in up to 2^20 particles
 constexpr float kLidarRange = 20.0f;   // kernel.cu:44
 constexpr int kFreeWeight = -1;        // kernel.cu:32
 constexpr int kOccupiedWeight = 4;     // kernel.cu:33
@@ -278,9 +279,11 @@ __device__ __forceinline__ float tile_scan4(const float e[4], float lm[4], float
 __global__ void __launch_bounds__(kScanThreads)
 k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__restrict__ fit,
                float *__restrict__ w, int n, int gidx0, int n_sync, int n_tiles,
-               float *__restrict__ tiles)
+               float *tiles, int fuse_prefix, int n_global, float *__restrict__ prefix,
+               FrameResult *__restrict__ res, int write_pose, int *__restrict__ done_counter)
 {
     __shared__ float s_wtot[8], s_wmax[8];
+    __shared__ int s_last;
     int gmin, gmax, best; float pose[3];
     reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
     const int rng = gmax - gmin;
@@ -307,6 +310,31 @@ k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__re
     for (int k = 0; k < 4; k++)
         if (base + k < n) lm_out[base + k] = lm[k];
     if (threadIdx.x == 0) { tiles[blockIdx.x] = t1; tiles[n_tiles + blockIdx.x] = t2; }
+    if (!fuse_prefix) return;
+    // single-GPU engines: the last block to finish also does k_prefix's job (global tile prefix in
+    // tile order, Neff, resample decision, robotPos)
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1; }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ float s_t[2 * kFusedPrefixMaxTiles];
+    for (int t = threadIdx.x; t < 2 * n_tiles; t += blockDim.x) s_t[t] = __ldcg(&tiles[t]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float p = 0.0f, p2 = 0.0f;
+        prefix[0] = 0.0f;
+        for (int t = 0; t < n_tiles; t++) {
+            p = __fadd_rn(p, s_t[t]);
+            p2 = __fadd_rn(p2, s_t[n_tiles + t]);
+            prefix[t + 1] = p;
+        }
+        const float neff = __fdiv_rn(__fmul_rn(p, p), p2);
+        if (write_pose) { res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2]; }
+        res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
+        res->sum_w = p; res->sum_w2 = p2; res->neff = neff;
+        res->resampled = ((double)neff < 0.7 * (double)n_global) ? 1 : 0;
+        *done_counter = 0;
+    }
 }
 
 // global tile prefixes (sequential in global tile order), Neff (kernel.cu:472), the resample

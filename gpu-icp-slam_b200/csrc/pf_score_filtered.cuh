@@ -90,7 +90,7 @@ k_beam_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle, 
 }
 
 // Fast scoring: block = 128 particles (one per thread) x one slice of the dense fast-beam list.
-// partial layout: [kFastSlices + 1][n]  (last row = slow beams, written by k_score_slow).
+// partial layout: [kFastSlices + 1][n]  (last row = slow beams: block row kFastSlices).
 __global__ void __launch_bounds__(kFastThreads)
 k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict__ x,
              const float *__restrict__ y, const float *__restrict__ th, int n,
@@ -99,6 +99,21 @@ k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict
              int *__restrict__ counters)
 {
     const float *__restrict__ scan = sp->scan;
+    if (blockIdx.y == kFastSlices) {
+        // extra block row: the slow beams (r >= 20 m, sentinel, NaN), exact for every particle; usually 0-3
+        const int p = blockIdx.x * kFastThreads + threadIdx.x;
+        if (p >= n) return;
+        const int ns = wk->ns;
+        int acc = 0;
+        if (ns > 0) {
+            const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
+            const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
+            const float px = x[p], py = y[p], pth = th[p];
+            for (int k = 0; k < ns; k++) { const int j = wk->slow[k]; acc += eval_exact(grid, g, c0x, c0y, px, py, pth, angle[j], scan[j]); }
+        }
+        partial[(size_t)kFastSlices * n + p] = acc;
+        return;
+    }
     __shared__ float4 s_const[(kMaxBeams + kFastSlices - 1) / kFastSlices];
     __shared__ unsigned s_queue[kQueueCap];
     __shared__ float s_pose[3][kFastThreads];
@@ -176,30 +191,6 @@ k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict
     if (tid == 0 && s_qn) atomicAdd(&counters[2], s_qn);
 }
 
-// Slow beams (r >= 20 m, sentinel, NaN): exact evaluation for every particle.  Usually 0-3 beams.
-__global__ void __launch_bounds__(256)
-k_score_slow(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict__ x,
-             const float *__restrict__ y, const float *__restrict__ th, int n,
-             const StepParams *__restrict__ sp, const float *__restrict__ angle,
-             const ScoreFilteredWork *__restrict__ wk, int *__restrict__ partial_slow)
-{
-    const float *__restrict__ scan = sp->scan;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const int ns = wk->ns;
-    int acc = 0;
-    if (ns > 0) {
-        const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
-        const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
-        const float px = x[p], py = y[p], pth = th[p];
-        for (int k = 0; k < ns; k++) {
-            const int j = wk->slow[k];
-            acc += eval_exact(grid, g, c0x, c0y, px, py, pth, angle[j], scan[j]);
-        }
-    }
-    partial_slow[p] = acc;
-}
-
 // fit[p] = sum of the slice partials; per-block (1024 particles) min / max-key partials
 __global__ void __launch_bounds__(256)
 k_score_combine(const int *__restrict__ partial, int n, int gidx0, int *__restrict__ fit,
@@ -247,18 +238,16 @@ static int score_filtered_launch(const int8_t *grid, MapGeom g, const float *x, 
                                  cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
     k_beam_prep<<<1, 1024, 0, stream>>>(scan, angle, n_beams, g, wk);
-    dim3 grid_fast((n + kFastThreads - 1) / kFastThreads, kFastSlices);
+    dim3 grid_fast((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);   // last row = slow beams
     if (ev0) cudaEventRecord(ev0, stream);
     k_score_fast<<<grid_fast, kFastThreads, 0, stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
                                                          partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
-    k_score_slow<<<(n + 255) / 256, 256, 0, stream>>>(grid, g, x, y, th, n, scan, angle, wk,
-                                                      partial + (size_t)kFastSlices * n);
     const int nblk = (n + kTile - 1) / kTile;
     k_score_combine<<<nblk, 256, 0, stream>>>(partial, n, gidx0, fit, blk_min, blk_maxkey);
     k_extrema<<<1, 1024, 0, stream>>>(blk_min, blk_maxkey, nblk, x, y, th, gidx0, ext_local);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return 5;
+    return 4;
 }
 
 }  // namespace pf

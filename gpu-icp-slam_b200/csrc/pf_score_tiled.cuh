@@ -12,12 +12,12 @@
 //   * 2^-16-cell fixed point relative to the window origin inside the float mantissa (magic 2^23):
 //     two packed FFMA2 give both axes; the cell byte of each axis is byte 2 of the result, so ONE
 //     PRMT builds the shared-memory offset (x*256 + y) and one LDS.S8 fetches the cell;
-//   * the rounding guard band (+-128 units = +-1.95e-3 cell, error bound 44 units) is
-//     "byte 1 == 0"; uncertain pairs set a bit in a per-particle 32-bit mask (one bit per beam of
+//   * the rounding guard band (+-64 units = +-9.8e-4 cell, error bound 38 units) is
+//     "bits 7..15 == 0"; uncertain pairs set a bit in a per-particle 32-bit mask (one bit per beam of
 //     the chunk), are compacted into a shared-memory queue after the chunk and re-evaluated with
 //     the reference's exact expression;
 //   * beams whose conservative box does not fit the chunk window (depth discontinuities, wide
-//     clouds) go to the v2 LDG kernel (k_score_fast), out-of-domain beams to k_score_slow.
+//     clouds) go to the v2 LDG kernel (k_score_fast), out-of-domain beams to its exact row.
 #pragma once
 #include <cuda.h>
 
@@ -39,7 +39,7 @@ constexpr int kTiledY = 6;                  // chunk-interleaved blocks per part
 constexpr int kTiledQueueCap = 2048;
 constexpr float kMagicT = 8388608.0f;       // 2^23
 constexpr int kFracT = 16;
-constexpr float kGuardT = 128.0f;           // units of 2^-16 cell
+constexpr float kGuardT = 64.0f;            // units of 2^-16 cell; band test = bits 7..15 zero (error bound 38)
 constexpr int kBoxMargin = 2;               // cells added around the conservative hit box
 
 struct TileChunk { int x0, y0, count, pad; };
@@ -113,7 +113,7 @@ __global__ void k_init_beam_trig(const float *__restrict__ angle, int n_beams, d
 }
 
 // Per-frame preparation (one block, 1024 threads, up to 2048 beams): classify every beam as
-//   slow  (outside the fast domain: r >= 20 m, sentinel, NaN)        -> wk->slow   (k_score_slow)
+//   slow  (outside the fast domain: r >= 20 m, sentinel, NaN)        -> wk->slow   (k_score_fast, exact row)
 //   tiled (conservative hit box fits its chunk's 128x128 window)    -> tw chunks  (k_score_tiled)
 //   wide  (fast domain, but does not fit)                           -> wk->fconst (k_score_fast)
 __global__ void __launch_bounds__(1024)
@@ -444,9 +444,9 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 const uint32_t idx = prmt(bx, by, 0xBB26u);
                 const int v = (int)tile[idx + (idx >> 6)];
                 asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                    "and.b32 t, %2, 0xff00;\n\t"
+                    "and.b32 t, %2, 0xff80;\n\t"
                     "setp.eq.u32 p, t, 0;\n\t"
-                    "and.b32 t, %3, 0xff00;\n\t"
+                    "and.b32 t, %3, 0xff80;\n\t"
                     "setp.eq.or.u32 p, t, 0, p;\n\t"
                     "@p or.b32 %0, %0, %4;\n\t"
                     "@!p add.s32 %1, %1, %5;\n\t}"
@@ -493,10 +493,13 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
 // fit[p] = sum of n_rows partial rows; per-256-particle min / max-key partials
 __global__ void __launch_bounds__(256)
 k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gidx0, int *__restrict__ fit,
-                     int *__restrict__ blk_min, long long *__restrict__ blk_maxkey)
+                     int *blk_min, long long *blk_maxkey, const float *__restrict__ x,
+                     const float *__restrict__ y, const float *__restrict__ th, Extrema *__restrict__ ext_out,
+                     int *__restrict__ done_counter)
 {
     __shared__ int smin[8];
     __shared__ long long smax[8];
+    __shared__ int s_last;
     int mn = 0x7fffffff;
     long long mk = (long long)0x8000000000000000ull;
     {
@@ -519,6 +522,36 @@ k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gid
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; w++) { mn = min(mn, smin[w]); mk = smax[w] > mk ? smax[w] : mk; }
         blk_min[blockIdx.x] = mn; blk_maxkey[blockIdx.x] = mk;
+        __threadfence();
+        s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block: thrust::minmax_element's result over all blocks (k_extrema folded in)
+    __threadfence();
+    mn = 0x7fffffff; mk = (long long)0x8000000000000000ull;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        mn = min(mn, __ldcg(&blk_min[i]));
+        const long long t = __ldcg(&blk_maxkey[i]);
+        mk = t > mk ? t : mk;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        long long t = __shfl_xor_sync(0xffffffffu, mk, o);
+        mk = t > mk ? t : mk;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { mn = min(mn, smin[w]); mk = smax[w] > mk ? smax[w] : mk; }
+        const int best = (int)(0xFFFFFFFFu - (uint32_t)(mk & 0xFFFFFFFFll));
+        Extrema e;
+        e.fit_min = mn; e.fit_max = (int)(mk >> 32); e.best_gidx = best;
+        e.x = x[best - gidx0]; e.y = y[best - gidx0]; e.th = th[best - gidx0];
+        e.pad0 = 0; e.pad1 = 0;
+        *ext_out = e;
+        *done_counter = 0;
     }
 }
 
@@ -544,7 +577,7 @@ static int make_grid_tensor_map(CUtensorMap *out, const int8_t *grid, int map_w,
     return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-inline int score_tiled_rows() { return kTiledY + kFastSlices + 1; }
+inline int score_tiled_rows() { return kTiledY + kFastSlices + 1; }   // tiled rows, wide-beam rows, slow-beam row
 
 static int score_tiled_setup()
 {
@@ -570,16 +603,14 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
     if (ev0) cudaEventRecord(ev0, stream);
     k_score_tiled<<<gt, kTiledThreads, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
-    dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices);
+    dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);          // last row = slow beams
     k_score_fast<<<gf, kFastThreads, 0, stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
                                                   partial + (size_t)kTiledY * n, counters);
-    k_score_slow<<<(n + 255) / 256, 256, 0, stream>>>(grid, g, x, y, th, n, scan, angle, wk,
-                                                      partial + (size_t)(kTiledY + kFastSlices) * n);
     const int nblk = (n + 255) / 256;
-    k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey);
-    k_extrema<<<1, 1024, 0, stream>>>(blk_min, blk_maxkey, nblk, x, y, th, gidx0, ext_local);
+    k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey,
+                                                   x, y, th, ext_local, counters + 4);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return nl;
+    return nl - 2;
 }
 
 }  // namespace pf

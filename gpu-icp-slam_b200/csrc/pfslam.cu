@@ -70,6 +70,7 @@ struct pfslam_engine {
     int *score_partial = nullptr;
     TiledWork *twork = nullptr;
     double2 *angle_cs = nullptr;
+    bool prefix_fused = false;
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
@@ -470,8 +471,12 @@ int pfslam_phase_weights(pfslam_engine *e)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     const int n_sync = (e->cfg.quirks & PFSLAM_QUIRK_Q1_HALF_WEIGHT_SYNC) ? (e->n_global + 1) / 2 : e->n_global;
+    // single-GPU grid path: the prefix step rides in the same launch (the kd path needs ICP in between)
+    const int fuse = (e->n_ranks == 1 && e->cfg.path == PFSLAM_PATH_GRID2D && e->n_tiles <= kFusedPrefixMaxTiles) ? 1 : 0;
+    e->prefix_fused = fuse != 0;
     k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(e->ext_all, e->n_ranks, e->fit, e->w, e->n,
-                                                               e->gidx0, n_sync, e->n_tiles, e->tiles_local);
+                                                               e->gidx0, n_sync, e->n_tiles, e->tiles_local, fuse,
+                                                               e->n_global, e->prefix, e->res, 1, e->counters + 5);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
@@ -479,6 +484,7 @@ int pfslam_phase_weights(pfslam_engine *e)
 
 static int launch_prefix(pfslam_engine *e)
 {
+    if (e->prefix_fused) { e->prefix_fused = false; return PFSLAM_OK; }   // done by k_weights_scan's last block
     const int nt = e->n_tiles * e->n_ranks;
     k_prefix<<<1, 1024, sizeof(float) * 2 * nt, e->stream>>>(e->ext_all, e->n_ranks, e->tiles_all, e->n_tiles,
                                                              e->tiles_block, e->n_global, e->prefix, e->res,

@@ -183,7 +183,7 @@ def test_graph_and_plain_launch_paths_agree(scans):
         assert np.array_equal(a.get_grid(), b.get_grid())
         xa, xb = a.get_particles(), b.get_particles()
         assert all(np.array_equal(bits(u), bits(v)) for u, v in zip(xa, xb))
-        assert a.launch_count > 39 * 10
+        assert a.launch_count > 39 * 5
 
 
 def test_reference_named_interface(scans):
