@@ -99,6 +99,7 @@ struct pfslam_engine {
     bool use_graph = true;
     int graph_kernels = 0;
     bool in_capture = false;
+    bool external_params = false;
     // in-step kernel timing
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -128,7 +129,7 @@ static int param_slot_used(pfslam_engine *e)
 // make the device StepParams equal (scan, frame) for the kernels enqueued after this call
 static int push_params(pfslam_engine *e, const float *scan, int frame)
 {
-    if (e->in_capture) return PFSLAM_OK;       // the graph's own copy node does it
+    if (e->in_capture || e->external_params) return PFSLAM_OK;   // a graph's copy node / the host does it
     if (e->cur.scan == scan && e->cur.frame == frame && e->n_param_pushes) return PFSLAM_OK;
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
@@ -336,6 +337,26 @@ int pfslam_set_stream(pfslam_engine *e, void *cuda_stream)
     // the legacy default stream cannot be captured into a graph: plain launches there
     e->use_graph = cuda_stream != nullptr && cuda_stream != (void *)cudaStreamLegacy;
     return PFSLAM_OK;
+}
+
+int pfslam_set_external_params(pfslam_engine *e, int32_t on)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->external_params = on != 0;
+    return PFSLAM_OK;
+}
+
+int pfslam_set_params(pfslam_engine *e, const float *scan_dev, int32_t frame)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    StepParams *slot = nullptr;
+    int rc = next_param_slot(e, &slot);
+    if (rc) return rc;
+    slot->scan = scan_dev ? scan_dev : e->scan; slot->frame = frame; slot->pad = 0;
+    CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
+    e->cur = *slot;
+    return param_slot_used(e);
 }
 
 int pfslam_synchronize(pfslam_engine *e)

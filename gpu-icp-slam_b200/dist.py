@@ -70,8 +70,36 @@ class ShardedParticleFilter:
             self.engine = engine_factory(self.n, **kw)
             self.t = self.engine.exchange_tensors()
 
+        self._graph = None
+        self._graph_launches = 0
+        self._replays = 0
+
     # -- one frame; nothing here synchronises the host ---------------------------------------------
+    def enable_graph(self):
+        """Capture the whole sharded step -- the engine's kernels AND the three all-gathers -- into one
+        CUDA graph (CUDA engines only; run a few eager steps first so NCCL is initialised).  Each
+        later step is a 16-byte parameter copy + one graph replay."""
+        import torch
+        e = self.engine
+        e.set_external_params(True)
+        e.set_params(None, 0)
+        torch.cuda.synchronize()
+        before = e.launch_count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=torch.cuda.current_stream()):
+            self._phases(None, 0)
+        self._graph_launches = e.launch_count - before
+        self._graph = graph
+
     def step_device(self, scan_dev_ptr, frame):
+        if self._graph is not None:
+            self.engine.set_params(scan_dev_ptr, frame)
+            self._graph.replay()
+            self._replays += 1
+            return
+        self._phases(scan_dev_ptr, frame)
+
+    def _phases(self, scan_dev_ptr, frame):
         e, t, d, g = self.engine, self.t, self.dist, self.group
         e.phase_motion(frame)
         _all_gather(d, t["pose_all"], t["pose_local"], g)       # pre-resample snapshot of every shard
@@ -90,7 +118,7 @@ class ShardedParticleFilter:
 
     @property
     def launch_count(self):
-        return self.engine.launch_count
+        return self.engine.launch_count + self._replays * self._graph_launches
 
     def close(self):
         self.engine.close()

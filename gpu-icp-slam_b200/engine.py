@@ -79,6 +79,8 @@ _SIGS = {
     "pfslam_phase_weights": (C.c_int, [C.c_void_p]),
     "pfslam_phase_map": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pfslam_phase_resample": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pfslam_set_external_params": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pfslam_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "pfslam_update_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfslam_score_particles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfslam_get_particles": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4),
@@ -277,6 +279,12 @@ class ParticleFilter:
 
     def phase_resample(self, frame):
         self._check(self._lib.pfslam_phase_resample(self._h, int(frame)))
+
+    def set_external_params(self, on=True):
+        self._check(self._lib.pfslam_set_external_params(self._h, 1 if on else 0))
+
+    def set_params(self, scan_dev_ptr, frame):
+        self._check(self._lib.pfslam_set_params(self._h, scan_dev_ptr, int(frame)))
 
     def synchronize(self):
         self._check(self._lib.pfslam_synchronize(self._h))

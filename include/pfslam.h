@@ -106,6 +106,13 @@ int  pfslam_phase_map(pfslam_engine *e, const float *scan_dev);                 
 /* ... all-gather PFSLAM_BUF_TILES_LOCAL -> _ALL, PFSLAM_BUF_POSE_LOCAL -> _ALL ... */
 int  pfslam_phase_resample(pfslam_engine *e, int32_t frame);                       /* kernel.cu:472-486 */
 
+/* Hosts that capture the phase calls into their own CUDA graph (dist.py does, together with the
+ * all-gathers) switch the engine to external parameters: the phases then stop pushing {scan, frame}
+ * themselves and read whatever the last pfslam_set_params put in the device StepParams -- a
+ * stream-ordered 16-byte copy issued before each graph replay. */
+int  pfslam_set_external_params(pfslam_engine *e, int32_t on);
+int  pfslam_set_params(pfslam_engine *e, const float *scan_dev, int32_t frame);
+
 /* occupancy-grid update alone (PFUpdateMap, kernel.cu:551) for an explicit pose */
 int  pfslam_update_grid(pfslam_engine *e, const float *scan_host, const float pose[3]);
 /* scoring alone (kernEvaluateParticles, kernel.cu:277): fit_out[n_particles] on the host */

@@ -29,6 +29,8 @@ def main():
     pf = ShardedParticleFilter(n_total // world, device=local)
     got = []
     for f in range(1, frames + 1):
+        if f == 4 and os.environ.get("PF_GRAPH", "0") == "1":
+            pf.enable_graph()                 # frames 4.. run as one captured graph incl. the all-gathers
         r = pf.step(scans[f], f)
         got.append(list(r.pose) + [r.fit_min, r.fit_max, r.best_index, r.neff, r.resampled, r.n_free_cells, r.n_wall_cells])
     grid = pf.engine.get_grid().reshape(-1)
