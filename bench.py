@@ -20,6 +20,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 N_BEAMS = 1081
 METRIC = "lidar_frames_per_sec_at_65536_particles_per_gpu"
