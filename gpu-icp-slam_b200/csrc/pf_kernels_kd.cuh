@@ -43,20 +43,33 @@ __device__ __forceinline__ float kd_dist(float qx, float qy, float qz, float nx,
     return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
 }
 
+__device__ __forceinline__ float kd_dist2(float qx, float qy, float qz, float nx, float ny, float nz)
+{
+    const float dx = __fsub_rn(nx, qx), dy = __fsub_rn(ny, qy), dz = __fsub_rn(nz, qz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
 // kernel.cu:924-972 findCorrespondenceIndexKD: descend by split plane tracking the best node, then
 // while improved look across the best node's PARENT plane once.  Q9: stop at the root.
+// The reference compares sqrt'ed distances (`d < bestDist`).  sqrt_rn is monotone, so d2 >= best2
+// implies d >= bestDist and the test is false without taking the root; only when d2 < best2 is the
+// root taken and the reference's comparison applied (two squared distances can round to one root).
 template <bool kCoherent>
 __device__ __forceinline__ int kd_nn(const KdNode *__restrict__ tree, float qx, float qy, float qz)
 {
     KdNode t = kCoherent ? kd_load_cg(tree, 0) : kd_load(tree, 0);
-    float bestDist = kd_dist(qx, qy, qz, t.x, t.y, t.z);
+    float best2 = kd_dist2(qx, qy, qz, t.x, t.y, t.z);
+    float bestDist = __fsqrt_rn(best2);
     int bestIdx = 0, bestParent = t.parent, head = 0;
     bool explored = false;
     for (;;) {
         while (head >= 0) {
             t = kCoherent ? kd_load_cg(tree, head) : kd_load(tree, head);
-            const float d = kd_dist(qx, qy, qz, t.x, t.y, t.z);
-            if (d < bestDist) { bestDist = d; bestIdx = head; bestParent = t.parent; explored = false; }
+            const float d2 = kd_dist2(qx, qy, qz, t.x, t.y, t.z);
+            if (d2 < best2) {
+                const float d = __fsqrt_rn(d2);
+                if (d < bestDist) { bestDist = d; best2 = d2; bestIdx = head; bestParent = t.parent; explored = false; }
+            }
             const bool branch = t.axis == 0 ? qx < t.x : t.axis == 1 ? qy < t.y : t.axis == 2 ? qz < t.z : false;
             head = branch ? t.left : t.right;
         }
@@ -84,7 +97,9 @@ __global__ void k_kd_nn(const KdNode *__restrict__ tree, const KdState *__restri
 // kernel.cu:1198-1308 kernEvaluateParticlesKD.  Node weights are integers (0, -100, +-1, +4, clamp
 // +-113), so the float sum of the reference is an exact integer and the grid path's integer
 // extrema / weight kernels are reused unchanged (the float overload's `int min`, Q5, is exact too).
-// block = 8 warps, lane = particle, warp w takes beams w, w+8, ...
+// block = 8 warps, lane = particle, warp w takes beams w, w+8, ...  (Interleaving 4 walks per thread
+// for memory-level parallelism was measured SLOWER, 5.5 vs 3.7 ms: the kernel is bound by divergent
+// instruction issue, not by load latency.)
 __global__ void __launch_bounds__(256)
 k_score_kd(const KdNode *__restrict__ tree, const float *__restrict__ x, const float *__restrict__ y,
            const float *__restrict__ th, int n, int gidx0, const StepParams *__restrict__ sp,
