@@ -228,7 +228,8 @@ def run_ours(args):
 
     if world > 1:
         from gpu_icp_slam_b200.dist import ShardedParticleFilter
-        pf = ShardedParticleFilter(n, device=local_rank)
+        pf = ShardedParticleFilter(n, device=local_rank, exchange=args.exchange,
+                                   path=g.PATH_KD if kd else g.PATH_GRID2D)
     else:
         pf = g.ParticleFilter(n, device=local_rank, path=g.PATH_KD if kd else g.PATH_GRID2D)
         pf.set_stream(stream.cuda_stream)
@@ -340,7 +341,10 @@ def run_ours(args):
                        "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS,
                        "score_mode": "tiled (TMA-staged smem windows, bit-exact)", "l2_flush": "256 MiB memset between timed steps (untimed)",
                        "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
-                       "parallelism": "particles sharded %d-way, map replicated" % world},
+                       "parallelism": "particles sharded %d-way, map replicated" % world,
+                       "exchange": ("none (single GPU)" if world == 1 else
+                                    "in-kernel stores/loads over NVLink peer memory, whole step = 1 CUDA graph per rank" if args.exchange == "peer"
+                                    else "3 NCCL all-gathers between the step's phases")},
             "value_back_to_back": K / (b2b_ms * 1e-3) * scale,
             "wall_s_timed_region": t_wall,
             "e2e": {"value": K / (e2e_ms * 1e-3) * scale, "unit": UNIT,
@@ -373,6 +377,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graph", action="store_true",
                     help="multi-GPU: capture the sharded step (kernels + all-gathers) in one CUDA graph (experimental)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
+                    help="multi-GPU transport: kernels over NVLink peer memory (default) or NCCL all-gathers between phases")
     ap.add_argument("--path", default="grid2d", choices=["grid2d", "kd"], help="map representation (BASELINE configs 2 / 3)")
     args = ap.parse_args()
     if args.impl == "reference":

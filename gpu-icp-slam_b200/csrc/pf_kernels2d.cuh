@@ -5,6 +5,7 @@
 // inline (paths relative to michaelwillett/GPU-ICP-SLAM src/).
 #pragma once
 #include "pf_arith.cuh"
+#include "pf_xchg.cuh"
 
 namespace pf {
 
@@ -29,6 +30,7 @@ struct FrameResult {
     float sum_w, sum_w2, neff;
     int   resampled, n_free, n_wall, n_slow;
     int   kd_size, kd_ins;
+    int   xchg_timeout;        // sharded engines: a peer-exchange wait ran into its time limit this frame
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
@@ -36,14 +38,7 @@ struct FrameResult {
 struct StepParams {
     const float *scan;   // this frame's ranges (device)
     int frame;           // frame number (seeds, kernel.cu:380, :434)
-    int pad;
-};
-
-// extrema record exchanged between ranks: 8 words
-struct Extrema {
-    int   fit_min, fit_max, best_gidx;
-    float x, y, th;
-    int   pad0, pad1;
+    int seq;             // step sequence number (peer-exchange flags and buffer parity, pf_xchg.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -60,10 +55,12 @@ __device__ __forceinline__ float order_float(int k)
 }
 
 // Also reduces the post-noise pose bounds of the cloud (ordered-int min/max of x, y, theta) into
-// bounds[6] for the tiled scorer's window placement.
+// bounds[6] for the tiled scorer's window placement, and writes the pre-resample snapshot the
+// resampler gathers from -- `snap` [parity][x | y | theta], null when a host all-gathers it.
 __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
-         const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds)
+         const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds,
+         float *__restrict__ snap, long long snap_stride, int parity_mask)
 {
     __shared__ int s_b[6];
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
@@ -78,6 +75,10 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
         float nt = pf_normal(st, 0.01f);
         const float vx = __fadd_rn(x[i], nx), vy = __fadd_rn(y[i], ny), vt = __fadd_rn(th[i], nt);
         x[i] = vx; y[i] = vy; th[i] = vt;
+        if (snap) {
+            float *sn = snap + (long long)(sp->seq & parity_mask) * snap_stride;
+            sn[i] = vx; sn[n + i] = vy; sn[2 * n + i] = vt;
+        }
         lo[0] = hi[0] = float_order(vx); lo[1] = hi[1] = float_order(vy); lo[2] = hi[2] = float_order(vt);
     }
 #pragma unroll
@@ -177,7 +178,7 @@ k_score_exact(const int8_t *__restrict__ grid, MapGeom g, const float *__restric
 __global__ void __launch_bounds__(1024)
 k_extrema(const int *__restrict__ blk_min, const long long *__restrict__ blk_maxkey, int n_blk,
           const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
-          int gidx0, Extrema *__restrict__ out)
+          int gidx0, Extrema *__restrict__ out, const Xchg xc, const StepParams *__restrict__ sp)
 {
     __shared__ int smin[32];
     __shared__ long long smax[32];
@@ -203,7 +204,7 @@ k_extrema(const int *__restrict__ blk_min, const long long *__restrict__ blk_max
         e.fit_min = mn; e.fit_max = (int)(mk >> 32); e.best_gidx = best;
         e.x = x[best - gidx0]; e.y = y[best - gidx0]; e.th = th[best - gidx0];
         e.pad0 = 0; e.pad1 = 0;
-        *out = e;
+        xc_publish_extrema(xc, out, e, sp->seq);
     }
 }
 
@@ -211,17 +212,18 @@ k_extrema(const int *__restrict__ blk_min, const long long *__restrict__ blk_max
 __device__ __forceinline__ void reduce_extrema(const Extrema *__restrict__ all, int n_ranks,
                                                int &gmin, int &gmax, int &best, float pose[3])
 {
-    gmin = all[0].fit_min;
-    long long mk = extrema_key(all[0].fit_max, all[0].best_gidx);
-    int br = 0;
+    Extrema b = xc_load_extrema(all);
+    gmin = b.fit_min;
+    long long mk = extrema_key(b.fit_max, b.best_gidx);
     for (int r = 1; r < n_ranks; r++) {
-        gmin = min(gmin, all[r].fit_min);
-        long long t = extrema_key(all[r].fit_max, all[r].best_gidx);
-        if (t > mk) { mk = t; br = r; }
+        const Extrema e = xc_load_extrema(all + r);
+        gmin = min(gmin, e.fit_min);
+        long long t = extrema_key(e.fit_max, e.best_gidx);
+        if (t > mk) { mk = t; b = e; }
     }
     gmax = (int)(mk >> 32);
-    best = all[br].best_gidx;
-    pose[0] = all[br].x; pose[1] = all[br].y; pose[2] = all[br].th;
+    best = b.best_gidx;
+    pose[0] = b.x; pose[1] = b.y; pose[2] = b.th;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -275,17 +277,27 @@ __device__ __forceinline__ float tile_scan4(const float e[4], float lm[4], float
 // c = 1/(float)(max-min) when max > min (kernel.cu:329-331); SURVEY Q1: only the first
 // ceil(N/2) particles' new weights persist (kernel.cu:337).  Then the per-tile scans that feed
 // Neff (kernel.cu:456-472) and the resampling CDF (kernel.cu:478).
-// tiles layout: [tsum_w (n_tiles)][tsum_w2 (n_tiles)][lm (n)]
+// A tiles block is [tsum_w (n_tiles)][tsum_w2 (n_tiles)] at xc.sum_off and lm (n) at xc.lm_off.
+// Sharded over peer memory (xc.parity_mask): the kernel first waits for every rank's extrema, and
+// stores its tile results straight into every rank's exchange region; the last block raises the flags.
 __global__ void __launch_bounds__(kScanThreads)
-k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__restrict__ fit,
+k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__restrict__ fit,
                float *__restrict__ w, int n, int gidx0, int n_sync, int n_tiles,
-               float *tiles, int fuse_prefix, int n_global, float *__restrict__ prefix,
+               float *tiles_local, int fuse_prefix, int n_global, float *__restrict__ prefix,
                FrameResult *__restrict__ res, int write_pose, int *__restrict__ done_counter)
 {
     __shared__ float s_wtot[8], s_wmax[8];
-    __shared__ int s_last;
+    __shared__ int s_last, s_ok;
+    const int seq = sp->seq;
+    if (xc.parity_mask) {
+        if (threadIdx.x == 0) {
+            s_ok = xc_wait(xc, kXcExt, seq) ? 1 : 0;
+            if (!s_ok && blockIdx.x == 0) res->xchg_timeout = 1;
+        }
+        __syncthreads();
+    }
     int gmin, gmax, best; float pose[3];
-    reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
+    reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose);
     const int rng = gmax - gmin;
     const float c = rng > 0 ? __fdiv_rn(1.0f, (float)rng) : 1.0f;
     const float fmin = (float)gmin;
@@ -305,20 +317,38 @@ k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__re
     }
     float t2 = tile_scan4(q, lm2, s_wtot, s_wmax);
     float t1 = tile_scan4(e, lm, s_wtot, s_wmax);
-    float *lm_out = tiles + 2 * n_tiles;
+    if (!xc.parity_mask) {
+        float *lm_out = tiles_local + xc.lm_off;
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (base + k < n) lm_out[base + k] = lm[k];
-    if (threadIdx.x == 0) { tiles[blockIdx.x] = t1; tiles[n_tiles + blockIdx.x] = t2; }
-    if (!fuse_prefix) return;
-    // single-GPU engines: the last block to finish also does k_prefix's job (global tile prefix in
-    // tile order, Neff, resample decision, robotPos)
-    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1; }
+        for (int k = 0; k < 4; k++)
+            if (base + k < n) lm_out[base + k] = lm[k];
+        if (threadIdx.x == 0) { tiles_local[xc.sum_off + blockIdx.x] = t1; tiles_local[xc.sum_off + n_tiles + blockIdx.x] = t2; }
+        if (!fuse_prefix) return;
+    } else {
+        // shards are tile-aligned (n % kTile == 0): every thread owns 4 valid, 16-byte-aligned items
+        for (int r = 0; r < xc.n_ranks; r++) {
+            float *blk = reinterpret_cast<float *>(xc.peer[r] + xc.off_tiles) +
+                         ((long long)(seq & 1) * xc.n_ranks + xc.rank) * xc.tiles_block;
+            *reinterpret_cast<float4 *>(blk + xc.lm_off + base) = make_float4(lm[0], lm[1], lm[2], lm[3]);
+            if (threadIdx.x == 0) { blk[xc.sum_off + blockIdx.x] = t1; blk[xc.sum_off + n_tiles + blockIdx.x] = t2; }
+        }
+        __syncthreads();          // thread 0's system fence below then covers the whole block's stores
+    }
+    if (threadIdx.x == 0) {
+        if (xc.parity_mask) __threadfence_system(); else __threadfence();
+        s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
+    if (xc.parity_mask) {
+        if (threadIdx.x == 0) { *done_counter = 0; xc_signal(xc, kXcTiles, seq); }
+        return;
+    }
+    // single-GPU engines: the last block to finish also does k_prefix's job (global tile prefix in
+    // tile order, Neff, resample decision, robotPos)
     __threadfence();
     __shared__ float s_t[2 * kFusedPrefixMaxTiles];
-    for (int t = threadIdx.x; t < 2 * n_tiles; t += blockDim.x) s_t[t] = __ldcg(&tiles[t]);
+    for (int t = threadIdx.x; t < 2 * n_tiles; t += blockDim.x) s_t[t] = __ldcg(&tiles_local[xc.sum_off + t]);
     __syncthreads();
     if (threadIdx.x == 0) {
         float p = 0.0f, p2 = 0.0f;
@@ -338,20 +368,29 @@ k_weights_scan(const Extrema *__restrict__ ext_all, int n_ranks, const int *__re
 }
 
 // global tile prefixes (sequential in global tile order), Neff (kernel.cu:472), the resample
-// decision (kernel.cu:474) and robotPos (kernel.cu:338).  tiles_all: n_ranks blocks of
-// [tsum_w][tsum_w2][lm]; prefix: n_tiles_global+1 floats.
+// decision (kernel.cu:474) and robotPos (kernel.cu:338).  prefix: n_tiles_global+1 floats.
+// Sharded over peer memory: waits for every rank's tile results first.
 __global__ void __launch_bounds__(1024)
-k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restrict__ tiles_all,
-         int n_tiles_local, long long tiles_block_floats, int n_global,
+k_prefix(const Xchg xc, const StepParams *__restrict__ sp, int n_tiles_local, int n_global,
          float *__restrict__ prefix, FrameResult *__restrict__ res, int write_pose)
 {
     extern __shared__ float s_t[];            // 2 * n_tiles_global
-    const int nt = n_ranks * n_tiles_local;
+    __shared__ int s_ok;
+    const int seq = sp->seq;
+    if (xc.parity_mask) {
+        if (threadIdx.x == 0) {
+            s_ok = xc_wait(xc, kXcTiles, seq) ? 1 : 0;
+            if (!s_ok) res->xchg_timeout = 1;
+        }
+        __syncthreads();
+    }
+    const float *tiles_all = xc_tiles(xc, seq);
+    const int nt = xc.n_ranks * n_tiles_local;
     for (int t = threadIdx.x; t < nt; t += blockDim.x) {
         int r = t / n_tiles_local, tl = t - r * n_tiles_local;
-        const float *blk = tiles_all + (long long)r * tiles_block_floats;
-        s_t[t] = blk[tl];
-        s_t[nt + t] = blk[n_tiles_local + tl];
+        const float *blk = tiles_all + (long long)r * xc.tiles_block + xc.sum_off;
+        s_t[t] = __ldcg(&blk[tl]);
+        s_t[nt + t] = __ldcg(&blk[n_tiles_local + tl]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -364,7 +403,7 @@ k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restri
         }
         float neff = __fdiv_rn(__fmul_rn(p, p), p2);
         int gmin, gmax, best; float pose[3];
-        reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
+        reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose);
         if (write_pose) { res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2]; }
         res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
         res->sum_w = p; res->sum_w2 = p2; res->neff = neff;
@@ -373,18 +412,19 @@ k_prefix(const Extrema *__restrict__ ext_all, int n_ranks, const float *__restri
 }
 
 // resample: kernel.cu:429-444 kernWeightedSample (seed (Neff, frame, i)), gathering
-// from the pre-resample snapshot pose_all.  The CDF is prefix[tile] + lm[i]; it is
-// monotone, so the two-level binary search returns the reference's linear-scan index.
+// from the pre-resample snapshot.  The CDF is prefix[tile] + lm[i]; it is monotone, so
+// the two-level binary search returns the reference's linear-scan index.  Sharded over peer memory
+// the drawn particle's pose is loaded from its owner's snapshot (xc.pose_src[owner], NVLink).
 __global__ void __launch_bounds__(256)
-k_resample(const FrameResult *__restrict__ res, const float *__restrict__ prefix,
-           const float *__restrict__ tiles_all, int n_tiles_local, long long tiles_block_floats,
-           const float *__restrict__ pose_all, int n_local, int n_global, int gidx0,
+k_resample(const Xchg xc, const FrameResult *__restrict__ res, const float *__restrict__ prefix,
+           int n_tiles_local, int n_local, int n_global, int gidx0,
            const StepParams *__restrict__ sp, float *__restrict__ x, float *__restrict__ y,
            float *__restrict__ th, float *__restrict__ w)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local || !res->resampled) return;
-    const int frame = sp->frame;
+    const int frame = sp->frame, seq = sp->seq;
+    const float *tiles_all = xc_tiles(xc, seq);
     const int nt = (n_global + kTile - 1) / kTile;   // == n_ranks * n_tiles_local when sharded
     uint32_t st = pf_minstd_seed(pf_seed((int)res->neff, frame, gidx0 + i));
     uint32_t u = pf_minstd_next(st) - 1u;
@@ -397,7 +437,7 @@ k_resample(const FrameResult *__restrict__ res, const float *__restrict__ prefix
     else {
         const int r = (lo * kTile) / n_local;
         const int l0 = lo * kTile - r * n_local;
-        const float *lm = tiles_all + (long long)r * tiles_block_floats + 2 * n_tiles_local + l0;
+        const float *lm = tiles_all + (long long)r * xc.tiles_block + xc.lm_off + l0;
         const float pt = prefix[lo];
         int cnt = min(kTile, n_global - lo * kTile);
         int a = 0, b = cnt;
@@ -405,7 +445,7 @@ k_resample(const FrameResult *__restrict__ res, const float *__restrict__ prefix
         src = lo * kTile + (a < cnt ? a : cnt - 1);
     }
     const int r = src / n_local, l = src - r * n_local;
-    const float *pp = pose_all + (long long)r * 3 * n_local;
+    const float *pp = xc.pose_src[r] + (long long)(seq & xc.parity_mask) * xc.snap_stride;
     x[i] = pp[l]; y[i] = pp[n_local + l]; th[i] = pp[2 * n_local + l];
     w[i] = 1.0f;
 }

@@ -174,7 +174,7 @@ __device__ __forceinline__ float icp_warp_sum(const float *v, int n, int lane)
 // reference reads in kernGetWallsKD), NN correspondences, means, cross-covariance, planar rotation,
 // robotPos = best particle pose + (t.x, t.y, theta).
 __global__ void __launch_bounds__(1024)
-k_icp(const KdNode *__restrict__ tree, const Extrema *__restrict__ ext_all, int n_ranks,
+k_icp(const KdNode *__restrict__ tree, const Xchg xc,
       const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams, FrameResult *__restrict__ res)
 {
     extern __shared__ float s_f[];           // tar x|y, cor x|y, prod : 5 * n_beams
@@ -215,7 +215,7 @@ k_icp(const KdNode *__restrict__ tree, const Extrema *__restrict__ ext_all, int 
         const float t_x = __fsub_rn(s_m[2], __fmaf_rn(cs, s_m[0], -__fmul_rn(sn, s_m[1])));
         const float t_y = __fsub_rn(s_m[3], __fmaf_rn(sn, s_m[0], __fmul_rn(cs, s_m[1])));
         int gmin, gmax, best; float pose[3];
-        reduce_extrema(ext_all, n_ranks, gmin, gmax, best, pose);
+        reduce_extrema(xc_ext(xc, sp->seq), xc.n_ranks, gmin, gmax, best, pose);   // k_weights_scan already waited for it
         res->pose[0] = __fadd_rn(pose[0], t_x);
         res->pose[1] = __fadd_rn(pose[1], t_y);
         res->pose[2] = __fadd_rn(pose[2], pf_asinf(sn));

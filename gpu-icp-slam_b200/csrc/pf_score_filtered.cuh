@@ -234,7 +234,7 @@ static int score_filtered_launch(const int8_t *grid, MapGeom g, const float *x, 
                                  const float *th, int n, int gidx0, const StepParams *scan,
                                  const float *angle, int n_beams, int *fit, int *blk_min,
                                  long long *blk_maxkey, Extrema *ext_local, ScoreFilteredWork *wk,
-                                 int *partial, int *counters, cudaStream_t stream,
+                                 int *partial, int *counters, const Xchg &xc, cudaStream_t stream,
                                  cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
     k_beam_prep<<<1, 1024, 0, stream>>>(scan, angle, n_beams, g, wk);
@@ -245,7 +245,7 @@ static int score_filtered_launch(const int8_t *grid, MapGeom g, const float *x, 
     if (ev1) cudaEventRecord(ev1, stream);
     const int nblk = (n + kTile - 1) / kTile;
     k_score_combine<<<nblk, 256, 0, stream>>>(partial, n, gidx0, fit, blk_min, blk_maxkey);
-    k_extrema<<<1, 1024, 0, stream>>>(blk_min, blk_maxkey, nblk, x, y, th, gidx0, ext_local);
+    k_extrema<<<1, 1024, 0, stream>>>(blk_min, blk_maxkey, nblk, x, y, th, gidx0, ext_local, xc, scan);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return 4;
 }

@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256)
 k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gidx0, int *__restrict__ fit,
                      int *blk_min, long long *blk_maxkey, const float *__restrict__ x,
                      const float *__restrict__ y, const float *__restrict__ th, Extrema *__restrict__ ext_out,
-                     int *__restrict__ done_counter)
+                     int *__restrict__ done_counter, const Xchg xc, const StepParams *__restrict__ sp)
 {
     __shared__ int smin[8];
     __shared__ long long smax[8];
@@ -550,8 +550,8 @@ k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gid
         e.fit_min = mn; e.fit_max = (int)(mk >> 32); e.best_gidx = best;
         e.x = x[best - gidx0]; e.y = y[best - gidx0]; e.th = th[best - gidx0];
         e.pad0 = 0; e.pad1 = 0;
-        *ext_out = e;
         *done_counter = 0;
+        xc_publish_extrema(xc, ext_out, e, sp->seq);
     }
 }
 
@@ -589,7 +589,7 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                               const float *th, int n, int gidx0, const StepParams *scan, const float *angle, int n_beams,
                               int *fit, int *blk_min, long long *blk_maxkey, Extrema *ext_local,
                               ScoreFilteredWork *wk, TiledWork *tw, const double2 *angle_cs, bool bounds_valid,
-                              int *partial, int *counters, cudaStream_t stream,
+                              int *partial, int *counters, const Xchg &xc, cudaStream_t stream,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
     int nl = 6;
@@ -608,7 +608,7 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                                                   partial + (size_t)kTiledY * n, counters);
     const int nblk = (n + 255) / 256;
     k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey,
-                                                   x, y, th, ext_local, counters + 4);
+                                                   x, y, th, ext_local, counters + 4, xc, scan);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return nl - 2;
 }

@@ -1,0 +1,133 @@
+// pf_xchg.cuh -- how the shards of one particle filter (one engine per GPU) exchange the few words
+// a frame needs, from INSIDE the step's kernels, over NVLink peer memory.
+//
+// The reference is single-GPU; sharding is new.  Per frame a shard needs from the others
+//   (1) the score extrema {min, max, first arg-max, its pose}              32 B per rank
+//   (2) per-tile weight sums and the tile-local CDF values                  ~4 B per particle
+//   (3) the pre-resample pose of whatever particle its resampler draws     12 B per local particle
+// Every engine owns one "exchange region" (a single cudaMalloc, IPC-exportable) with the same layout
+// on every rank.  Producers STORE (1) and (2) straight into every peer's region from the kernel that
+// computes them (k_score_combine_rows / k_extrema, k_weights_scan), then raise a per-(kind, source
+// rank) flag in the peer's region with the step's sequence number; the first consumer kernel of the
+// step spins (bounded) on its own region's flags.  (3) is PULLED: k_resample loads the drawn
+// particle's pose from the owner's snapshot over NVLink.  No NCCL call, no host round trip: the
+// sharded step is the same single CUDA graph as the single-GPU step.
+//
+// Buffers are double-buffered by step parity.  That is enough because the shards run in lock step:
+// a rank publishes extrema(s+1) only after it has seen every rank's tiles(s), and tiles(s+1) only
+// after every rank's extrema(s+1) -- so nobody can be more than one publication ahead of a reader.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pf {
+
+constexpr int kMaxRanks = 16;
+constexpr int kXcExt = 0, kXcTiles = 1;      // flag kinds
+
+// extrema record exchanged between ranks: 8 words
+struct Extrema {
+    int   fit_min, fit_max, best_gidx;
+    float x, y, th;
+    int   pad0, pad1;
+};
+
+// Passed by value to the kernels that produce or consume exchanged data.  parity_mask == 0: single
+// GPU, or a host that runs its own collectives between the phases (dist.py over torch.distributed);
+// then ext_all / tiles_all are plain local buffers and nothing is published or awaited.
+struct Xchg {
+    int n_ranks, rank;
+    int parity_mask;              // 1 = peer-memory exchange
+    unsigned timeout_ms;          // bound on every flag wait
+    long long tiles_block;        // floats per (parity, source rank) tiles block
+    long long sum_off, lm_off;    // offsets of [tsum_w | tsum_w2] and lm[] inside a tiles block
+    long long snap_stride;        // floats between the two parities of a pose snapshot (3 n)
+    // this rank's view (own region when parity_mask, else the engine's local / host-gathered buffers)
+    Extrema *ext_all;             // [parity][kMaxRanks]
+    float   *tiles_all;           // [parity][n_ranks][tiles_block]
+    float   *snap;                // own pre-resample snapshot [parity][x | y | theta]; null: host gathers
+    int     *flags;               // [kind][kMaxRanks] sequence numbers, written by the peers
+    // every rank's region (peer memory) and the byte offsets of the parts inside a region
+    unsigned char *peer[kMaxRanks];
+    long long off_ext, off_tiles, off_flags;
+    const float *pose_src[kMaxRanks];   // resample gather source per owner rank (parity 0)
+};
+
+__device__ __forceinline__ unsigned long long xc_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int xc_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void xc_st_release(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ Extrema *xc_ext(const Xchg &xc, int seq)
+{
+    return xc.ext_all + (seq & xc.parity_mask) * kMaxRanks;
+}
+__device__ __forceinline__ float *xc_tiles(const Xchg &xc, int seq)
+{
+    return xc.tiles_all + (long long)(seq & xc.parity_mask) * xc.n_ranks * xc.tiles_block;
+}
+
+// One thread: wait until every rank's flag of `kind` has reached this step's sequence number.
+// Returns false on timeout (the caller records it in the frame result; nothing hangs).
+__device__ __forceinline__ bool xc_wait(const Xchg &xc, int kind, int seq)
+{
+    if (!xc.parity_mask) return true;
+    const int *f = xc.flags + kind * kMaxRanks;
+    const unsigned long long t0 = xc_now_ns();
+    const unsigned long long limit = (unsigned long long)xc.timeout_ms * 1000000ull;
+    bool ok = true;
+    for (int r = 0; r < xc.n_ranks && ok; r++) {
+        unsigned spins = 0;
+        while (xc_ld_acquire(f + r) - seq < 0) {
+            if ((++spins & 255u) == 0u && xc_now_ns() - t0 > limit) { ok = false; break; }
+        }
+    }
+    return ok;
+}
+
+// One thread, after the data stores (and a block barrier if other threads made them): make the
+// stores visible system-wide, then raise this rank's flag in every peer's region.
+__device__ __forceinline__ void xc_signal(const Xchg &xc, int kind, int seq)
+{
+    __threadfence_system();
+    for (int r = 0; r < xc.n_ranks; r++)
+        xc_st_release(reinterpret_cast<int *>(xc.peer[r] + xc.off_flags) + kind * kMaxRanks + xc.rank, seq);
+}
+
+// Extrema of this shard -> ext_local (local modes) or slot [parity][rank] of every peer's region.
+__device__ __forceinline__ void xc_publish_extrema(const Xchg &xc, Extrema *ext_local, const Extrema &e, int seq)
+{
+    if (!xc.parity_mask) { *ext_local = e; return; }
+    const int4 a = make_int4(e.fit_min, e.fit_max, e.best_gidx, __float_as_int(e.x));
+    const int4 b = make_int4(__float_as_int(e.y), __float_as_int(e.th), 0, 0);
+    for (int r = 0; r < xc.n_ranks; r++) {
+        int4 *dst = reinterpret_cast<int4 *>(reinterpret_cast<Extrema *>(xc.peer[r] + xc.off_ext) +
+                                             (seq & 1) * kMaxRanks + xc.rank);
+        dst[0] = a; dst[1] = b;
+    }
+    xc_signal(xc, kXcExt, seq);
+}
+
+__device__ __forceinline__ Extrema xc_load_extrema(const Extrema *p)
+{
+    const int4 a = __ldcg(reinterpret_cast<const int4 *>(p));
+    const int4 b = __ldcg(reinterpret_cast<const int4 *>(p) + 1);
+    Extrema e;
+    e.fit_min = a.x; e.fit_max = a.y; e.best_gidx = a.z; e.x = __int_as_float(a.w);
+    e.y = __int_as_float(b.x); e.th = __int_as_float(b.y); e.pad0 = 0; e.pad1 = 0;
+    return e;
+}
+
+}  // namespace pf

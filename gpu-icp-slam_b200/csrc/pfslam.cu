@@ -100,6 +100,15 @@ struct pfslam_engine {
     int graph_kernels = 0;
     bool in_capture = false;
     bool external_params = false;
+    // shard exchange (pf_xchg.cuh): xc_host = single GPU / host-run collectives, xc_p2p = peer memory
+    unsigned char *xreg = nullptr; size_t xreg_bytes = 0;
+    size_t xoff_flags = 0, xoff_ext = 0, xoff_tiles = 0, xoff_snap = 0;
+    Xchg xc_host{}, xc_p2p{};
+    const Xchg *cur_xc = nullptr;
+    void *peer_base[kMaxRanks] = {};
+    bool peer_ipc[kMaxRanks] = {};
+    bool p2p_ready = false;
+    int seq = 0;                   // step sequence number (StepParams.seq)
     // in-step kernel timing
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -130,11 +139,11 @@ static int param_slot_used(pfslam_engine *e)
 static int push_params(pfslam_engine *e, const float *scan, int frame)
 {
     if (e->in_capture || e->external_params) return PFSLAM_OK;   // a graph's copy node / the host does it
-    if (e->cur.scan == scan && e->cur.frame == frame && e->n_param_pushes) return PFSLAM_OK;
+    if (e->cur.scan == scan && e->cur.frame == frame && e->cur.seq == e->seq && e->n_param_pushes) return PFSLAM_OK;
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
     if (rc) return rc;
-    slot->scan = scan; slot->frame = frame; slot->pad = 0;
+    slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
     CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
     e->cur = *slot;
     return param_slot_used(e);
@@ -176,6 +185,8 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->angle_cs); cudaFree(e->sp);
     cudaFree(e->kd); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
     cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index);
+    for (int r = 0; r < kMaxRanks; r++) if (e->peer_ipc[r] && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
+    cudaFree(e->xreg);
     cudaFreeHost(e->h_sp);
     for (auto ev : e->lap_ev) if (ev) cudaEventDestroy(ev);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
@@ -217,6 +228,38 @@ static int engine_alloc(pfslam_engine *e)
     }
     CUDA_TRY(cudaMalloc(&e->pose_all, sizeof(float) * 3 * (size_t)n * e->n_ranks));
     CUDA_TRY(cudaMalloc(&e->prefix, sizeof(float) * ((size_t)e->n_tiles * e->n_ranks + 1)));
+    {   // single GPU, or a host that runs its own collectives between the phases
+        Xchg &h = e->xc_host;
+        h.n_ranks = e->n_ranks; h.rank = e->n_ranks > 1 ? e->gidx0 / n : 0; h.parity_mask = 0; h.timeout_ms = 0;
+        h.tiles_block = e->tiles_block; h.sum_off = 0; h.lm_off = 2ll * e->n_tiles; h.snap_stride = 0;
+        h.ext_all = e->ext_all; h.tiles_all = e->tiles_all;
+        h.snap = e->n_ranks == 1 ? e->pose_all : nullptr;
+        for (int r = 0; r < e->n_ranks && r < kMaxRanks; r++) h.pose_src[r] = e->pose_all + (size_t)r * 3 * n;
+        e->cur_xc = &e->xc_host;
+    }
+    if (e->n_ranks > 1) {
+        // the exchange region peers store into / load from (pf_xchg.cuh); same layout on every rank
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t tb = (size_t)n + (((size_t)2 * e->n_tiles + 3) & ~(size_t)3);
+        e->xoff_flags = 0;
+        e->xoff_ext = up(sizeof(int) * 2 * kMaxRanks);
+        e->xoff_tiles = up(e->xoff_ext + sizeof(Extrema) * 2 * kMaxRanks);
+        e->xoff_snap = up(e->xoff_tiles + sizeof(float) * 2 * e->n_ranks * tb);
+        e->xreg_bytes = up(e->xoff_snap + sizeof(float) * 2 * 3 * (size_t)n);
+        CUDA_TRY(cudaMalloc(&e->xreg, e->xreg_bytes));
+        CUDA_TRY(cudaMemsetAsync(e->xreg, 0, e->xreg_bytes, e->stream));
+        Xchg &x = e->xc_p2p;
+        x.n_ranks = e->n_ranks; x.rank = e->gidx0 / n; x.parity_mask = 1;
+        const char *to = getenv("PFSLAM_PEER_TIMEOUT_MS");
+        x.timeout_ms = to ? (unsigned)atoi(to) : 10000u;
+        x.tiles_block = (long long)tb; x.sum_off = n; x.lm_off = 0; x.snap_stride = 3ll * n;
+        x.ext_all = reinterpret_cast<Extrema *>(e->xreg + e->xoff_ext);
+        x.tiles_all = reinterpret_cast<float *>(e->xreg + e->xoff_tiles);
+        x.snap = reinterpret_cast<float *>(e->xreg + e->xoff_snap);
+        x.flags = reinterpret_cast<int *>(e->xreg + e->xoff_flags);
+        x.off_ext = (long long)e->xoff_ext; x.off_tiles = (long long)e->xoff_tiles; x.off_flags = (long long)e->xoff_flags;
+        e->peer_base[x.rank] = e->xreg;
+    }
     CUDA_TRY(cudaMalloc(&e->res, sizeof(FrameResult)));
     CUDA_TRY(cudaMalloc(&e->counters, sizeof(int) * 8));
     CUDA_TRY(cudaMalloc(&e->fwork, sizeof(ScoreFilteredWork)));
@@ -265,6 +308,24 @@ static int engine_alloc(pfslam_engine *e)
     return PFSLAM_OK;
 }
 
+// CUDA loads kernels lazily, and a first-use load can wait for the device to drain.  A sharded engine's
+// kernels spin on flags that another engine's (another stream's) kernels raise, so every kernel must be
+// resident before the first step: a load blocking behind a spinning kernel would stall its own peer.
+static int preload_kernels()
+{
+    cudaFuncAttributes a;
+#define PF_PRELOAD(k) CUDA_TRY(cudaFuncGetAttributes(&a, k))
+    PF_PRELOAD(k_motion); PF_PRELOAD(k_cloud_bounds); PF_PRELOAD(k_bounds_reset); PF_PRELOAD(k_tile_prep);
+    PF_PRELOAD(k_beam_prep); PF_PRELOAD(k_score_tiled); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
+    PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
+    PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
+    PF_PRELOAD(k_score_kd); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
+    PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
+    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn);
+#undef PF_PRELOAD
+    return PFSLAM_OK;
+}
+
 int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
 {
     if (!cfg || !out) return set_error(PFSLAM_ERR_ARG, "null argument");
@@ -282,8 +343,8 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
         return set_error(PFSLAM_ERR_ARG, "sharded engines need n_particles %% 1024 == 0 and equal shards");
     if (cfg->path != PFSLAM_PATH_GRID2D && cfg->path != PFSLAM_PATH_KD)
         return set_error(PFSLAM_ERR_ARG, "unknown path %d", cfg->path);
-    if (cfg->path == PFSLAM_PATH_KD && cfg->n_ranks != 1)
-        return set_error(PFSLAM_ERR_UNSUPPORTED, "the kd path is single-GPU in this build");
+    if (cfg->n_ranks > kMaxRanks)
+        return set_error(PFSLAM_ERR_UNSUPPORTED, "at most %d ranks", kMaxRanks);
     if (cfg->score_mode < PFSLAM_SCORE_EXACT || cfg->score_mode > PFSLAM_SCORE_TILED)
         return set_error(PFSLAM_ERR_ARG, "bad score_mode");
     int ndev = 0;
@@ -308,6 +369,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     e->own_stream = true;
     int rc = engine_alloc(e);
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
+    if ((rc = preload_kernels()) != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
     rc = score_filtered_setup(e->cfg.device);
     if (rc != 0) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "scoring kernel setup failed"); }
     // the fixed-point scorers need an integral map centre c0 = 0.5*scale/res and maps below 2048 cells;
@@ -353,10 +415,95 @@ int pfslam_set_params(pfslam_engine *e, const float *scan_dev, int32_t frame)
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
     if (rc) return rc;
-    slot->scan = scan_dev ? scan_dev : e->scan; slot->frame = frame; slot->pad = 0;
+    slot->scan = scan_dev ? scan_dev : e->scan; slot->frame = frame; slot->seq = e->seq;
     CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
     e->cur = *slot;
     return param_slot_used(e);
+}
+
+// ---- shard exchange over peer memory (pf_xchg.cuh) ----------------------------------------------
+int pfslam_exchange_region(pfslam_engine *e, void **dev_ptr, int64_t *bytes)
+{
+    if (!e || !dev_ptr || !bytes) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (!e->xreg) return set_error(PFSLAM_ERR_STATE, "single-rank engines have no exchange region");
+    *dev_ptr = e->xreg; *bytes = (int64_t)e->xreg_bytes;
+    return PFSLAM_OK;
+}
+
+int pfslam_ipc_export(pfslam_engine *e, void *handle_out)
+{
+    if (!e || !handle_out) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (!e->xreg) return set_error(PFSLAM_ERR_STATE, "single-rank engines have no exchange region");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == PFSLAM_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, e->xreg));
+    memcpy(handle_out, &h, sizeof h);
+    return PFSLAM_OK;
+}
+
+static int set_peer(pfslam_engine *e, int rank, void *base, bool ipc)
+{
+    if (rank < 0 || rank >= e->n_ranks) return set_error(PFSLAM_ERR_ARG, "rank %d of %d", rank, e->n_ranks);
+    if (rank == e->xc_p2p.rank) return PFSLAM_OK;          // own region is already in place
+    if (e->peer_ipc[rank] && e->peer_base[rank]) cudaIpcCloseMemHandle(e->peer_base[rank]);
+    e->peer_base[rank] = base; e->peer_ipc[rank] = ipc;
+    e->p2p_ready = false;
+    return PFSLAM_OK;
+}
+
+int pfslam_ipc_connect(pfslam_engine *e, int32_t rank, const void *handle)
+{
+    if (!e || !handle) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (!e->xreg) return set_error(PFSLAM_ERR_STATE, "single-rank engines have no exchange region");
+    if (rank == e->xc_p2p.rank) return PFSLAM_OK;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *base = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    return set_peer(e, rank, base, true);
+}
+
+int pfslam_connect_peer(pfslam_engine *e, int32_t rank, void *peer_region)
+{
+    if (!e || !peer_region) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (!e->xreg) return set_error(PFSLAM_ERR_STATE, "single-rank engines have no exchange region");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    cudaPointerAttributes at;
+    CUDA_TRY(cudaPointerGetAttributes(&at, peer_region));
+    if (at.type != cudaMemoryTypeDevice) return set_error(PFSLAM_ERR_ARG, "peer region is not device memory");
+    if (at.device != e->cfg.device) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, e->cfg.device, at.device));
+        if (!can) return set_error(PFSLAM_ERR_UNSUPPORTED, "device %d cannot access device %d", e->cfg.device, at.device);
+        cudaError_t ce = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled)
+            return set_error(PFSLAM_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+    }
+    return set_peer(e, rank, peer_region, false);
+}
+
+// All peers known: from now on pfslam_step / pfslam_step_async run the sharded step with the
+// exchange inside the kernels.  Callers barrier across ranks between this call and the first step.
+int pfslam_exchange_ready(pfslam_engine *e)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    if (!e->xreg) return set_error(PFSLAM_ERR_STATE, "single-rank engines have no exchange region");
+    for (int r = 0; r < e->n_ranks; r++)
+        if (!e->peer_base[r]) return set_error(PFSLAM_ERR_STATE, "rank %d is not connected", r);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < e->n_ranks; r++) {
+        e->xc_p2p.peer[r] = static_cast<unsigned char *>(e->peer_base[r]);
+        e->xc_p2p.pose_src[r] = reinterpret_cast<const float *>(e->xc_p2p.peer[r] + e->xoff_snap);
+    }
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    e->graph_failed = false;
+    e->p2p_ready = true;
+    return PFSLAM_OK;
 }
 
 int pfslam_synchronize(pfslam_engine *e)
@@ -379,23 +526,27 @@ int pfslam_upload_scan(pfslam_engine *e, const float *scan_host)
     return PFSLAM_OK;
 }
 
-int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
+static int ph_motion(pfslam_engine *e, int32_t frame)
 {
-    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
-    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds);
+    const Xchg &xc = *e->cur_xc;
+    // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
+    k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
+                                                         xc.snap, xc.snap_stride, xc.parity_mask);
     e->bounds_valid = true;
     e->launches++;
     CUDA_TRY(cudaGetLastError());
-    if (e->n_ranks == 1) {
-        // single GPU: the pre-resample snapshot is a device copy (multi-GPU hosts all-gather it)
-        CUDA_TRY(cudaMemcpyAsync(e->pose_all, e->x, sizeof(float) * 3 * e->n,
-                                 cudaMemcpyDeviceToDevice, e->stream));
-    }
     return PFSLAM_OK;
 }
 
-static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0, cudaEvent_t ev1)
+int pfslam_phase_motion(pfslam_engine *e, int32_t frame)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->cur_xc = &e->xc_host;
+    return ph_motion(e, frame);
+}
+
+static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0, cudaEvent_t ev1, const Xchg &xc)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     { int rc = push_params(e, scan_dev ? scan_dev : e->scan, e->cur.frame); if (rc) return rc; }
@@ -409,12 +560,12 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
         e->launches++;
         CUDA_TRY(cudaGetLastError());
         k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y,
-                                             e->th, e->gidx0, e->ext_local);
+                                             e->th, e->gidx0, e->ext_local, xc, e->sp);
         e->launches++;
     } else if (e->score_mode == PFSLAM_SCORE_TILED) {
         int nl = score_tiled_launch(e->tmap, e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                     e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
-                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, e->stream, ev0, ev1);
+                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->stream, ev0, ev1);
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
@@ -422,7 +573,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     } else {
         int nl = score_filtered_launch(e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                        e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local,
-                                       e->fwork, e->score_partial, e->counters, e->stream, ev0, ev1);
+                                       e->fwork, e->score_partial, e->counters, xc, e->stream, ev0, ev1);
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "filtered scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
         e->launches += nl;
@@ -431,13 +582,20 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     return PFSLAM_OK;
 }
 
+static int ph_score(pfslam_engine *e, const float *scan_dev)
+{
+    if (e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2) {
+        const int k = e->prof_n++;
+        return score_phase(e, scan_dev, e->prof_ev[2 * k], e->prof_ev[2 * k + 1], *e->cur_xc);
+    }
+    return score_phase(e, scan_dev, nullptr, nullptr, *e->cur_xc);
+}
+
 int pfslam_phase_score(pfslam_engine *e, const float *scan_dev)
 {
-    if (e && e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2) {
-        const int k = e->prof_n++;
-        return score_phase(e, scan_dev, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]);
-    }
-    return score_phase(e, scan_dev, nullptr, nullptr);
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->cur_xc = &e->xc_host;
+    return ph_score(e, scan_dev);
 }
 
 int pfslam_profile_enable(pfslam_engine *e, int32_t on)
@@ -476,7 +634,7 @@ int pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase)
     cudaEvent_t ev[4];
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
     CUDA_TRY(cudaEventRecord(ev[0], e->stream));
-    int rc = score_phase(e, nullptr, ev[1], ev[2]);
+    int rc = score_phase(e, nullptr, ev[1], ev[2], e->xc_host);
     if (rc == PFSLAM_OK) {
         cudaEventRecord(ev[3], e->stream);
         cudaError_t ce = cudaStreamSynchronize(e->stream);
@@ -488,14 +646,13 @@ int pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase)
     return rc;
 }
 
-int pfslam_phase_weights(pfslam_engine *e)
+static int ph_weights(pfslam_engine *e)
 {
-    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     const int n_sync = (e->cfg.quirks & PFSLAM_QUIRK_Q1_HALF_WEIGHT_SYNC) ? (e->n_global + 1) / 2 : e->n_global;
     // single-GPU grid path: the prefix step rides in the same launch (the kd path needs ICP in between)
     const int fuse = (e->n_ranks == 1 && e->cfg.path == PFSLAM_PATH_GRID2D && e->n_tiles <= kFusedPrefixMaxTiles) ? 1 : 0;
     e->prefix_fused = fuse != 0;
-    k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(e->ext_all, e->n_ranks, e->fit, e->w, e->n,
+    k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(*e->cur_xc, e->sp, e->fit, e->w, e->n,
                                                                e->gidx0, n_sync, e->n_tiles, e->tiles_local, fuse,
                                                                e->n_global, e->prefix, e->res, 1, e->counters + 5);
     e->launches++;
@@ -503,12 +660,18 @@ int pfslam_phase_weights(pfslam_engine *e)
     return PFSLAM_OK;
 }
 
+int pfslam_phase_weights(pfslam_engine *e)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->cur_xc = &e->xc_host;
+    return ph_weights(e);
+}
+
 static int launch_prefix(pfslam_engine *e)
 {
     if (e->prefix_fused) { e->prefix_fused = false; return PFSLAM_OK; }   // done by k_weights_scan's last block
     const int nt = e->n_tiles * e->n_ranks;
-    k_prefix<<<1, 1024, sizeof(float) * 2 * nt, e->stream>>>(e->ext_all, e->n_ranks, e->tiles_all, e->n_tiles,
-                                                             e->tiles_block, e->n_global, e->prefix, e->res,
+    k_prefix<<<1, 1024, sizeof(float) * 2 * nt, e->stream>>>(*e->cur_xc, e->sp, e->n_tiles, e->n_global, e->prefix, e->res,
                                                              e->cfg.path == PFSLAM_PATH_KD ? 0 : 1);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -533,25 +696,36 @@ static int launch_map(pfslam_engine *e)
 // sums, so it runs at the head of the resample phase; the map update then uses robotPos.  The
 // reference's order measurement -> map -> resample is preserved because the map update does not
 // read particle weights and the resample does not read the map.
-int pfslam_phase_map(pfslam_engine *e, const float *scan_dev)
+static int ph_map(pfslam_engine *e, const float *scan_dev)
 {
-    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     int rc = push_params(e, scan_dev ? scan_dev : e->scan, e->cur.frame);
     if (rc) return rc;
     if ((rc = launch_prefix(e))) return rc;
     return launch_map(e);
 }
 
-int pfslam_phase_resample(pfslam_engine *e, int32_t frame)
+int pfslam_phase_map(pfslam_engine *e, const float *scan_dev)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->cur_xc = &e->xc_host;
+    return ph_map(e, scan_dev);
+}
+
+static int ph_resample(pfslam_engine *e, int32_t frame)
+{
     { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
-    k_resample<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->res, e->prefix, e->tiles_all, e->n_tiles,
-                                                           e->tiles_block, e->pose_all, e->n, e->n_global,
+    k_resample<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(*e->cur_xc, e->res, e->prefix, e->n_tiles, e->n, e->n_global,
                                                            e->gidx0, e->sp, e->x, e->y, e->th, e->w);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
+}
+
+int pfslam_phase_resample(pfslam_engine *e, int32_t frame)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    e->cur_xc = &e->xc_host;
+    return ph_resample(e, frame);
 }
 
 
@@ -655,32 +829,33 @@ static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
         CUDA_TRY(cudaMemsetAsync(e->res, 0, sizeof(FrameResult), e->stream));      // robotPos = 0 (kernel.cu:1715)
         return kd_update_map(e);
     }
-    if ((rc = pfslam_phase_motion(e, frame))) return rc;
+    if ((rc = ph_motion(e, frame))) return rc;
     const bool prof = e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2;
     if (prof) cudaEventRecord(e->prof_ev[2 * e->prof_n], e->stream);
     k_score_kd<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
                                                          e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
     if (prof) { cudaEventRecord(e->prof_ev[2 * e->prof_n + 1], e->stream); e->prof_n++; }
-    k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y, e->th, e->gidx0, e->ext_local);
+    k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y, e->th, e->gidx0,
+                                         e->ext_local, *e->cur_xc, e->sp);
     e->launches += 2;
     e->bounds_valid = false;
-    if ((rc = pfslam_phase_weights(e))) return rc;
-    k_icp<<<1, 1024, sizeof(float) * 5 * e->cfg.n_beams, e->stream>>>(e->kd, e->ext_all, e->n_ranks, e->sp, e->angle,
+    if ((rc = ph_weights(e))) return rc;
+    k_icp<<<1, 1024, sizeof(float) * 5 * e->cfg.n_beams, e->stream>>>(e->kd, *e->cur_xc, e->sp, e->angle,
                                                                     e->cfg.n_beams, e->res);
     e->launches += 1;
     if ((rc = launch_prefix(e))) return rc;
     if ((rc = kd_update_map(e))) return rc;
-    return pfslam_phase_resample(e, frame);
+    return ph_resample(e, frame);
 }
 
 static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
 {
     int rc;
-    if ((rc = pfslam_phase_motion(e, frame))) return rc;
-    if ((rc = pfslam_phase_score(e, scan_dev))) return rc;
-    if ((rc = pfslam_phase_weights(e))) return rc;
-    if ((rc = pfslam_phase_map(e, scan_dev))) return rc;
-    if ((rc = pfslam_phase_resample(e, frame))) return rc;
+    if ((rc = ph_motion(e, frame))) return rc;
+    if ((rc = ph_score(e, scan_dev))) return rc;
+    if ((rc = ph_weights(e))) return rc;
+    if ((rc = ph_map(e, scan_dev))) return rc;
+    if ((rc = ph_resample(e, frame))) return rc;
     return PFSLAM_OK;
 }
 
@@ -724,9 +899,12 @@ static int build_graph(pfslam_engine *e)
 int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
 {
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
-    if (e->n_ranks != 1)
-        return set_error(PFSLAM_ERR_STATE, "sharded engines are stepped phase by phase by the multi-GPU host");
+    if (e->n_ranks != 1 && !e->p2p_ready)
+        return set_error(PFSLAM_ERR_STATE, "sharded engine without a peer exchange (pfslam_exchange_ready): "
+                                           "step it phase by phase from a host that runs the collectives");
     CUDA_TRY(cudaSetDevice(e->cfg.device));
+    e->cur_xc = e->p2p_ready ? &e->xc_p2p : &e->xc_host;
+    e->seq++;
     if (e->cfg.path == PFSLAM_PATH_KD) return kd_step(e, scan_dev, frame);
     const float *scan = scan_dev ? scan_dev : e->scan;
     if (e->use_graph && !e->prof_on && !e->graph_failed) {
@@ -735,7 +913,7 @@ int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
             StepParams *slot = nullptr;
             int rc = next_param_slot(e, &slot);
             if (rc) return rc;
-            slot->scan = scan; slot->frame = frame; slot->pad = 0;
+            slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
             CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(e->graph_exec, e->graph_param_node, e->sp, slot,
                                                         sizeof(StepParams), cudaMemcpyHostToDevice));
             CUDA_TRY(cudaGraphLaunch(e->graph_exec, e->stream));
@@ -758,6 +936,7 @@ static void copy_result(const FrameResult *r, pfslam_frame_result *out)
     out->resampled = r->resampled; out->n_free_cells = r->n_free; out->n_wall_cells = r->n_wall;
     out->n_slow_evals = r->n_slow;
     out->kd_size = r->kd_size; out->kd_inserted = r->kd_ins;
+    out->exchange_timeout = r->xchg_timeout;
 }
 
 int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
@@ -767,6 +946,8 @@ int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
     CUDA_TRY(cudaMemcpyAsync(e->h_res, e->res, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     copy_result(e->h_res, out);
+    if (e->h_res->xchg_timeout)
+        return set_error(PFSLAM_ERR_STATE, "peer exchange timed out (a shard stopped stepping, or the shards are out of step)");
     return PFSLAM_OK;
 }
 

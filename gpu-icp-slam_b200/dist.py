@@ -1,15 +1,22 @@
 """Multi-GPU particle filter: particles sharded N/R per GPU, map replicated.
 
-One process per GPU (torchrun); `torch.distributed` is the plumbing.  Per frame the shards exchange
-  1. the post-noise poses (all-gather, 12 B/particle) -- the resampler's pre-resample snapshot,
-  2. per-rank score extrema {min, max, first arg-max, its pose} (all-gather, 32 B/rank),
-  3. per-tile weight sums + tile-local CDF values (all-gather, ~4 B/particle),
+One process per GPU (torchrun); `torch.distributed` is the plumbing (rendezvous, the one-off exchange
+of IPC handles, barriers).  Per frame the shards need from each other
+  1. per-rank score extrema {min, max, first arg-max, its pose} (32 B/rank),
+  2. per-tile weight sums + tile-local CDF values (~4 B/particle),
+  3. the pre-resample poses the resampler draws (12 B/particle),
 and every rank then derives the identical global min/max/robotPos, Neff, resample decision, CDF
 and map update.  Random streams are seeded by GLOBAL particle index and every floating-point
 reduction has a fixed global tile order, so the trajectory is bit-identical for any rank count.
 
-`ShardedParticleFilter` drives any engine that implements the phase protocol of
-`engine.ParticleFilter` (the CUDA engine on GPUs; tests drive it with a CPU stand-in over gloo).
+Two transports:
+  * exchange="peer" (default on GPUs): the engines' kernels store 1 and 2 straight into the peers'
+    exchange regions over NVLink and pull 3 from the owner (csrc/pf_xchg.cuh); a frame is one CUDA
+    graph launch per rank, with no collective call and no host round trip.
+  * exchange="collective": the step's phases with three `all_gather_into_tensor` calls between them.
+    Any engine that implements the phase protocol of `engine.ParticleFilter` works (tests drive it
+    with a CPU stand-in over gloo); on GPUs it is the NCCL baseline the peer transport is measured
+    against.
 """
 import ctypes as C
 
@@ -49,7 +56,7 @@ def _all_gather(dist, out, inp, group):
 class ShardedParticleFilter:
     """The whole filter = world_size shards of `n_per_rank` particles, one per process."""
 
-    def __init__(self, n_per_rank, device=0, group=None, engine_factory=None, **engine_kw):
+    def __init__(self, n_per_rank, device=0, group=None, engine_factory=None, exchange=None, **engine_kw):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -61,12 +68,22 @@ class ShardedParticleFilter:
             raise _engine.PfslamError("sharded filters need n_per_rank % 1024 == 0 (tile-aligned shards)")
         kw = dict(n_particles_global=self.n_global, particle_offset=self.rank * self.n, n_ranks=self.world)
         kw.update(engine_kw)
+        self.exchange = exchange or ("peer" if engine_factory is None and self.world > 1 else "collective")
+        if self.exchange not in ("peer", "collective"):
+            raise _engine.PfslamError("exchange must be 'peer' or 'collective'")
         if engine_factory is None:
             import torch
             self.engine = _engine.ParticleFilter(self.n, device=device, **kw)
             self.engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
-            self.t = cuda_exchange_tensors(self.engine, device)
+            if self.world == 1:
+                self.exchange = "peer"          # a single shard is just the engine's own graph step
+            elif self.exchange == "peer":
+                self._connect_peers(device)
+            else:
+                self.t = cuda_exchange_tensors(self.engine, device)
         else:
+            if self.exchange == "peer":
+                raise _engine.PfslamError("the peer-memory exchange needs the CUDA engine")
             self.engine = engine_factory(self.n, **kw)
             self.t = self.engine.exchange_tensors()
 
@@ -74,12 +91,28 @@ class ShardedParticleFilter:
         self._graph_launches = 0
         self._replays = 0
 
+    def _connect_peers(self, device):
+        """one-off: all-gather the 64-byte IPC handles of the exchange regions, map every peer's region"""
+        import torch
+        mine = torch.frombuffer(bytearray(self.engine.ipc_export()), dtype=torch.uint8).to(torch.device("cuda", device))
+        allh = torch.empty(self.world * _engine.IPC_HANDLE_BYTES, dtype=torch.uint8, device=mine.device)
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        for r in range(self.world):
+            if r != self.rank:
+                self.engine.ipc_connect(r, raw[r * _engine.IPC_HANDLE_BYTES:(r + 1) * _engine.IPC_HANDLE_BYTES])
+        self.engine.exchange_ready()
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)      # nobody publishes before every region is mapped and zeroed
+
     # -- one frame; nothing here synchronises the host ---------------------------------------------
     def enable_graph(self):
         """Capture the whole sharded step -- the engine's kernels AND the three all-gathers -- into one
         CUDA graph (CUDA engines only; run a few eager steps first so NCCL is initialised).  Each
         later step is a 16-byte parameter copy + one graph replay."""
         import torch
+        if self.exchange == "peer":
+            return                      # the engine's own step is already one graph
         e = self.engine
         e.set_external_params(True)
         e.set_params(None, 0)
@@ -92,6 +125,9 @@ class ShardedParticleFilter:
         self._graph = graph
 
     def step_device(self, scan_dev_ptr, frame):
+        if self.exchange == "peer":
+            self.engine.step_async(frame, scan_dev_ptr)
+            return
         if self._graph is not None:
             self.engine.set_params(scan_dev_ptr, frame)
             self._graph.replay()
@@ -112,6 +148,8 @@ class ShardedParticleFilter:
 
     def step(self, scan_host, frame):
         """particleFilter(pbo, frame, lidar) for the sharded filter: host scan in, result out."""
+        if self.exchange == "peer":
+            return self.engine.step(scan_host, frame)
         self.engine.upload_scan(scan_host)
         self.step_device(None, frame)
         return self.engine.fetch_result()
@@ -121,4 +159,8 @@ class ShardedParticleFilter:
         return self.engine.launch_count + self._replays * self._graph_launches
 
     def close(self):
+        if self.exchange == "peer" and self.world > 1:
+            # peers may still be pulling poses from this rank's snapshot
+            self.engine.synchronize()
+            self.dist.barrier(group=self.group)
         self.engine.close()

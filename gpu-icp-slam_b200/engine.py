@@ -21,6 +21,7 @@ PATH_GRID2D, PATH_KD = 0, 1
 SCORE_EXACT, SCORE_FILTERED, SCORE_TILED = 0, 1, 2
 QUIRK_Q1 = 1
 QUIRKS_REFERENCE = QUIRK_Q1
+IPC_HANDLE_BYTES = 64
 BUF_EXTREMA_LOCAL, BUF_EXTREMA_ALL, BUF_TILES_LOCAL, BUF_TILES_ALL, BUF_POSE_LOCAL, BUF_POSE_ALL, BUF_SCAN = range(7)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -49,6 +50,7 @@ class FrameResult(C.Structure):
         ("best_index", C.c_int32), ("sum_w", C.c_float), ("sum_w2", C.c_float), ("neff", C.c_float),
         ("resampled", C.c_int32), ("n_free_cells", C.c_int32), ("n_wall_cells", C.c_int32),
         ("n_slow_evals", C.c_int32), ("kd_size", C.c_int32), ("kd_inserted", C.c_int32),
+        ("exchange_timeout", C.c_int32),
     ]
 
     def as_dict(self):
@@ -91,6 +93,11 @@ _SIGS = {
     "pfslam_get_pose": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pfslam_synchronize": (C.c_int, [C.c_void_p]),
     "pfslam_device_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "pfslam_exchange_region": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "pfslam_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pfslam_ipc_connect": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pfslam_connect_peer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pfslam_exchange_ready": (C.c_int, [C.c_void_p]),
     "pfslam_kd_nn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pfslam_get_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "pfslam_set_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
@@ -368,6 +375,28 @@ class ParticleFilter:
     def set_kd(self, nodes):
         a = np.ascontiguousarray(nodes, dtype=np.int32).reshape(-1, 8)
         self._check(self._lib.pfslam_set_kd(self._h, a.ctypes.data, a.shape[0]))
+
+    # -- shard exchange over peer memory (include/pfslam.h "multi-GPU") ---------------------------
+    def exchange_region(self):
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._check(self._lib.pfslam_exchange_region(self._h, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def ipc_export(self):
+        """the 64-byte CUDA IPC handle of this engine's exchange region"""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._lib.pfslam_ipc_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def ipc_connect(self, rank, handle):
+        buf = C.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES)
+        self._check(self._lib.pfslam_ipc_connect(self._h, int(rank), buf))
+
+    def connect_peer(self, rank, region_ptr):
+        self._check(self._lib.pfslam_connect_peer(self._h, int(rank), C.c_void_p(region_ptr)))
+
+    def exchange_ready(self):
+        self._check(self._lib.pfslam_exchange_ready(self._h))
 
     def device_buffer(self, which):
         ptr, nbytes = C.c_void_p(), C.c_int64()

@@ -74,6 +74,7 @@ typedef struct pfslam_frame_result {
     int32_t n_slow_evals;        /* (particle, beam) pairs the filtered scorer re-did exactly */
     int32_t kd_size;             /* kd path: nodes in the tree after this frame (kdSize, kernel.cu:80) */
     int32_t kd_inserted;         /* kd path: nodes inserted this frame */
+    int32_t exchange_timeout;    /* sharded engines: 1 once a peer-exchange wait hit its time limit (results invalid) */
 } pfslam_frame_result;
 
 /* ---- life cycle: particleFilterInit(Scene*) / particleFilterFree(), kernel.cu:107-178 ---- */
@@ -95,7 +96,7 @@ int  particleFilterStep(pfslam_engine *e, const float *scan, int32_t frame, floa
 int  pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame);
 int  pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out);
 
-/* ---- the step's phases, for multi-GPU hosts that run a collective between them and for
+/* ---- the step's phases, for multi-GPU hosts that run a collective between them (see "multi-GPU" below) and for
  * function-level parity tests.  All asynchronous on the engine stream. ---- */
 int  pfslam_upload_scan(pfslam_engine *e, const float *scan_host);                 /* kernel.cu:315 */
 int  pfslam_phase_motion(pfslam_engine *e, int32_t frame);                         /* kernel.cu:400 */
@@ -136,7 +137,26 @@ int  pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_
 int  pfslam_get_kd(pfslam_engine *e, void *nodes_out, int32_t cap, int32_t *n_nodes);
 int  pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes);
 
-/* ---- device buffers a multi-GPU host all-gathers between phases (device pointers, engine-owned) ---- */
+/* ---- multi-GPU: particles sharded N/R per engine, map replicated (new; the reference is single-GPU) ----
+ * Default transport: PEER MEMORY.  Every sharded engine (n_ranks > 1) owns one exchange region;
+ * once each engine knows the regions of all ranks, pfslam_step / pfslam_step_async run the whole
+ * sharded frame as one CUDA graph: the kernels store score extrema and weight-tile sums straight
+ * into the peers' regions over NVLink, raise per-rank sequence flags there, spin (bounded by
+ * PFSLAM_PEER_TIMEOUT_MS, default 10 000) on their own flags, and the resampler loads the drawn
+ * particle's pose from its owner.  No collective library call and no host round trip per frame.
+ * All ranks must step in lock step with the same frame numbers.  Sequence:
+ *   one process per GPU:  pfslam_ipc_export -> exchange the 64-byte handles (any transport) ->
+ *                         pfslam_ipc_connect for every other rank -> pfslam_exchange_ready -> barrier
+ *   engines in one process: pfslam_exchange_region + pfslam_connect_peer, then pfslam_exchange_ready */
+#define PFSLAM_IPC_HANDLE_BYTES 64
+int  pfslam_exchange_region(pfslam_engine *e, void **dev_ptr, int64_t *bytes);
+int  pfslam_ipc_export(pfslam_engine *e, void *handle_out /* PFSLAM_IPC_HANDLE_BYTES */);
+int  pfslam_ipc_connect(pfslam_engine *e, int32_t rank, const void *handle);
+int  pfslam_connect_peer(pfslam_engine *e, int32_t rank, void *peer_region);
+int  pfslam_exchange_ready(pfslam_engine *e);
+
+/* ---- alternative transport: device buffers a multi-GPU host all-gathers between the phase calls above
+ * (dist.py with exchange="collective": torch.distributed all_gather_into_tensor) ---- */
 #define PFSLAM_BUF_EXTREMA_LOCAL 0  /* 8 x 4 B: {min, max, argmax global idx, x, y, theta, 0, 0}   */
 #define PFSLAM_BUF_EXTREMA_ALL   1  /* n_ranks x 8 x 4 B                                            */
 #define PFSLAM_BUF_TILES_LOCAL   2  /* {tile sums of w, tile sums of w^2, lm[n]} float32, see bytes  */
