@@ -20,9 +20,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# keep stdout to the one JSON line: NCCL prints its version banner (and any debug output) to stdout
+# unless told otherwise
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ.pop("NCCL_DEBUG")
 
 N_BEAMS = 1081
 METRIC = "lidar_frames_per_sec_at_65536_particles_per_gpu"
@@ -304,6 +306,15 @@ def run_ours(args):
         eng.set_external_params(True)
         pf._graph = saved_graph
     ker = max(ker, 1e-6)
+    # per-kernel breakdown of serialised steps (plain launches, an event after every kernel), L2 flushed
+    laps = {}
+    if not kd and world == 1:
+        eng.profile_laps(True)
+        for k in range(min(K, 100)):
+            flush.fill_(k & 0xff)
+            step_async(W + k)
+        laps = eng.profile_laps_read()
+        eng.profile_laps(False)
     iso_ms = [eng.profile_score() for _ in range(10)] if not kd else [(0.0, 0.0)]
     r = eng.fetch_result()
 
@@ -355,6 +366,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker, "kernel_launches_timed": n_prof,
                          "kernel_ms_isolated": float(np.mean([a for a, _ in iso_ms])),
                          "scoring_phase_ms_isolated": float(np.mean([b for _, b in iso_ms]))},
+            "kernels_ms_serialised": {k: round(v[0], 5) for k, v in laps.items()},
             "clocks": clocks,
             "last_frame": {"neff": r.neff, "resampled": r.resampled, "n_slow_evals": r.n_slow_evals,
                            "slow_eval_frac": r.n_slow_evals / float(n * N_BEAMS), "kd_size": r.kd_size},

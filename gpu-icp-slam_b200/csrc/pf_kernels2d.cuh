@@ -4,10 +4,25 @@
 // resample, all on one stream with no host round trip.  Reference semantics per kernel are cited
 // inline (paths relative to michaelwillett/GPU-ICP-SLAM src/).
 #pragma once
+#include <vector>
+
 #include "pf_arith.cuh"
 #include "pf_xchg.cuh"
 
 namespace pf {
+
+// host side: per-kernel lap events of the serialised profiling step (pfslam_profile_laps)
+enum { kLapStart = -1, kLapMotion = 0, kLapTilePrep, kLapScoreTiled, kLapScoreFast, kLapCombine, kLapWeights,
+       kLapPrefix, kLapMapFree, kLapMapWall, kLapResample, kLapCount };
+struct LapRec {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> id;
+    int n = 0;
+    void mark(cudaStream_t s, int lap_id)
+    {
+        if (n < (int)ev.size()) { cudaEventRecord(ev[n], s); id[n] = lap_id; n++; }
+    }
+};
 
 constexpr int kTile = 1024;            // reduction / scan tile (pfslam order)
 constexpr int kScanThreads = 256;      // 8 warps x 32 lanes x 4 items
@@ -287,12 +302,12 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
                FrameResult *__restrict__ res, int write_pose, int *__restrict__ done_counter)
 {
     __shared__ float s_wtot[8], s_wmax[8];
-    __shared__ int s_last, s_ok;
+    __shared__ int s_last;
     const int seq = sp->seq;
     if (xc.parity_mask) {
-        if (threadIdx.x == 0) {
-            s_ok = xc_wait(xc, kXcExt, seq) ? 1 : 0;
-            if (!s_ok && blockIdx.x == 0) res->xchg_timeout = 1;
+        if (threadIdx.x < 32) {
+            const bool ok = xc_wait_warp(xc, kXcExt, seq);
+            if (!ok && blockIdx.x == 0 && threadIdx.x == 0) res->xchg_timeout = 1;
         }
         __syncthreads();
     }
@@ -375,12 +390,11 @@ k_prefix(const Xchg xc, const StepParams *__restrict__ sp, int n_tiles_local, in
          float *__restrict__ prefix, FrameResult *__restrict__ res, int write_pose)
 {
     extern __shared__ float s_t[];            // 2 * n_tiles_global
-    __shared__ int s_ok;
     const int seq = sp->seq;
     if (xc.parity_mask) {
-        if (threadIdx.x == 0) {
-            s_ok = xc_wait(xc, kXcTiles, seq) ? 1 : 0;
-            if (!s_ok) res->xchg_timeout = 1;
+        if (threadIdx.x < 32) {
+            const bool ok = xc_wait_warp(xc, kXcTiles, seq);
+            if (!ok && threadIdx.x == 0) res->xchg_timeout = 1;
         }
         __syncthreads();
     }
@@ -485,20 +499,40 @@ __device__ __forceinline__ int8_t clamp_add(int8_t v, int d)
 // The first thread to set a cell's bit this frame applies the -1 (== the reference's bool mask).
 // Each thread issues the bit-set atomics of up to 8 steps before touching the grid so their
 // latencies overlap.
+// robotPos for the map update: the frame result (explicit-pose entry point, phase-by-phase hosts), or --
+// when the map update runs as a branch of the step graph next to the weight/resample kernels -- the
+// best particle's pose straight from the exchanged extrema (== what k_prefix writes into the result).
+__device__ __forceinline__ void map_pose(const FrameResult *__restrict__ res, const Xchg &xc, int seq, int pose_from_ext,
+                                         float pose[3])
+{
+    if (pose_from_ext) {
+        int gmin, gmax, best;
+        reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose);
+    } else {
+        pose[0] = res->pose[0]; pose[1] = res->pose[1]; pose[2] = res->pose[2];
+    }
+}
+
 __global__ void __launch_bounds__(128)
-k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__ res,
+k_map_free(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle,
-           unsigned *__restrict__ free_bits, int *__restrict__ counters)
+           unsigned *__restrict__ free_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
     __shared__ int s_cnt;
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
-    int cx, cy; center_cell(g, res->pose[0], res->pose[1], cx, cy);
+    if (threadIdx.x == 0) s_cnt = 0;
+    if (pose_from_ext && xc.parity_mask && threadIdx.x < 32) {   // this branch does not follow k_weights_scan's wait
+        const bool ok = xc_wait_warp(xc, kXcExt, sp->seq);
+        if (!ok && blockIdx.x == 0 && threadIdx.x == 0) res->xchg_timeout = 1;
+    }
+    __syncthreads();
+    float pose[3];
+    map_pose(res, xc, sp->seq, pose_from_ext, pose);
+    int cx, cy; center_cell(g, pose[0], pose[1], cx, cy);
     float wx, wy;
     int mine = 0;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    if (beam_hit(g, res->pose, cx, cy, angle[j], scan[j], wx, wy)) {
+    if (beam_hit(g, pose, cx, cy, angle[j], scan[j], wx, wy)) {
         int sx = cx, sy = cy, ex = (int)wx, ey = (int)wy;
         const bool steep = abs(ey - sy) > abs(ex - sx);
         int t;
@@ -540,15 +574,17 @@ k_map_free(int8_t *__restrict__ grid, MapGeom g, const FrameResult *__restrict__
 __global__ void __launch_bounds__(128)
 k_map_wall(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
-           unsigned *__restrict__ wall_bits, int *__restrict__ counters)
+           unsigned *__restrict__ wall_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;
     if (j < n_beams) {
-        int cx, cy; center_cell(g, res->pose[0], res->pose[1], cx, cy);
+        float pose[3];
+        map_pose(res, xc, sp->seq, pose_from_ext, pose);     // k_map_free (same stream) already waited
+        int cx, cy; center_cell(g, pose[0], pose[1], cx, cy);
         float wx, wy;
-        if (beam_hit(g, res->pose, cx, cy, angle[j], scan[j], wx, wy)) {
+        if (beam_hit(g, pose, cx, cy, angle[j], scan[j], wx, wy)) {
             if (wx >= 0.0f && wx < (float)g.w && wy >= 0.0f && wy < (float)g.h) {
                 int idx = (int)__fmaf_rn(wx, (float)g.w, wy);
                 unsigned bit = 1u << (idx & 31);

@@ -585,32 +585,43 @@ static int score_tiled_setup()
 }
 
 // returns the number of kernels launched, or -1.  partial: score_tiled_rows()*n ints.
+// With an auxiliary stream the wide/slow-beam kernel (k_score_fast) runs NEXT TO the tiled kernel
+// (fork after k_tile_prep, join before the row combine); inside a stream capture this becomes two
+// parallel branches of the step graph.
 static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGeom g, const float *x, const float *y,
                               const float *th, int n, int gidx0, const StepParams *scan, const float *angle, int n_beams,
                               int *fit, int *blk_min, long long *blk_maxkey, Extrema *ext_local,
                               ScoreFilteredWork *wk, TiledWork *tw, const double2 *angle_cs, bool bounds_valid,
                               int *partial, int *counters, const Xchg &xc, cudaStream_t stream,
-                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
+                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
+                              cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
+                              LapRec *laps = nullptr)
 {
-    int nl = 6;
+    int nl = 4;
     if (!bounds_valid) {   // poses were not produced by k_motion this frame (test hooks): recompute
         k_bounds_reset<<<1, 32, 0, stream>>>(tw);
         k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw);
         nl += 2;
     }
     k_tile_prep<<<1, 1024, 0, stream>>>(scan, angle, angle_cs, n_beams, g, wk, tw);
+    if (laps) laps->mark(stream, kLapTilePrep);
+    if (aux) { cudaEventRecord(ev_fork, stream); cudaStreamWaitEvent(aux, ev_fork, 0); }
     dim3 gt((n + kTiledGroup - 1) / kTiledGroup, kTiledY);
     if (ev0) cudaEventRecord(ev0, stream);
     k_score_tiled<<<gt, kTiledThreads, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
+    if (laps) laps->mark(stream, kLapScoreTiled);
     dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);          // last row = slow beams
-    k_score_fast<<<gf, kFastThreads, 0, stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
-                                                  partial + (size_t)kTiledY * n, counters);
+    k_score_fast<<<gf, kFastThreads, 0, aux ? aux : stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
+                                                              partial + (size_t)kTiledY * n, counters);
+    if (laps) laps->mark(stream, kLapScoreFast);
+    if (aux) { cudaEventRecord(ev_join, aux); cudaStreamWaitEvent(stream, ev_join, 0); }
     const int nblk = (n + 255) / 256;
     k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey,
                                                    x, y, th, ext_local, counters + 4, xc, scan);
+    if (laps) laps->mark(stream, kLapCombine);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return nl - 2;
+    return nl;
 }
 
 }  // namespace pf

@@ -97,6 +97,25 @@ __device__ __forceinline__ bool xc_wait(const Xchg &xc, int kind, int seq)
     return ok;
 }
 
+// The same wait by a whole warp (all 32 lanes call it): lane r polls rank r's flag, so the wait costs
+// one round of latency whatever the rank count.
+__device__ __forceinline__ bool xc_wait_warp(const Xchg &xc, int kind, int seq)
+{
+    if (!xc.parity_mask) return true;
+    const int lane = threadIdx.x & 31;
+    const int *f = xc.flags + kind * kMaxRanks;
+    const unsigned long long t0 = xc_now_ns();
+    const unsigned long long limit = (unsigned long long)xc.timeout_ms * 1000000ull;
+    bool ok = true;
+    if (lane < xc.n_ranks) {
+        unsigned spins = 0;
+        while (xc_ld_acquire(f + lane) - seq < 0) {
+            if ((++spins & 255u) == 0u && xc_now_ns() - t0 > limit) { ok = false; break; }
+        }
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
 // One thread, after the data stores (and a block barrier if other threads made them): make the
 // stores visible system-wide, then raise this rank's flag in every peer's region.
 __device__ __forceinline__ void xc_signal(const Xchg &xc, int kind, int seq)

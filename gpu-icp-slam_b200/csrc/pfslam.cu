@@ -109,6 +109,14 @@ struct pfslam_engine {
     bool peer_ipc[kMaxRanks] = {};
     bool p2p_ready = false;
     int seq = 0;                   // step sequence number (StepParams.seq)
+    // independent kernels of a step run side by side: an auxiliary stream forked / joined with events
+    // (branches of the step graph once captured)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    bool overlap = true;
+    // serialised per-kernel timing (pfslam_profile_laps)
+    bool laps_on = false;
+    LapRec laps;
     // in-step kernel timing
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -193,6 +201,10 @@ int pfslam_destroy(pfslam_engine *e)
     if (e->graph) cudaGraphDestroy(e->graph);
     cudaFreeHost(e->h_scan); cudaFreeHost(e->h_res);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    for (auto ev : e->laps.ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 3; i++) if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
+    for (int i = 0; i < 2; i++) if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    if (e->aux) cudaStreamDestroy(e->aux);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return PFSLAM_OK;
@@ -367,6 +379,15 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete e; return set_error(PFSLAM_ERR_CUDA, "stream: %s", cudaGetErrorString(ce)); }
     e->own_stream = true;
+    {   // the side branches yield to the critical path
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        ce = cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, lo);
+    }
+    for (int i = 0; i < 3 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+    if (ce != cudaSuccess) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "aux stream: %s", cudaGetErrorString(ce)); }
+    { const char *no = getenv("PFSLAM_NO_OVERLAP"); e->overlap = !(no && atoi(no) != 0); }
     int rc = engine_alloc(e);
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
     if ((rc = preload_kernels()) != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
@@ -533,6 +554,7 @@ static int ph_motion(pfslam_engine *e, int32_t frame)
     // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
     k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
                                                          xc.snap, xc.snap_stride, xc.parity_mask);
+    if (e->laps_on) e->laps.mark(e->stream, kLapMotion);
     e->bounds_valid = true;
     e->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -551,6 +573,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
     { int rc = push_params(e, scan_dev ? scan_dev : e->scan, e->cur.frame); if (rc) return rc; }
     const StepParams *scan = e->sp;
+    const bool use_aux = e->overlap && !e->laps_on;
     if (e->score_mode == PFSLAM_SCORE_EXACT) {
         if (ev0) cudaEventRecord(ev0, e->stream);
         k_score_exact<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(
@@ -565,7 +588,8 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     } else if (e->score_mode == PFSLAM_SCORE_TILED) {
         int nl = score_tiled_launch(e->tmap, e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                     e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
-                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->stream, ev0, ev1);
+                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->stream, ev0, ev1,
+                                    use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr);
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
@@ -655,8 +679,46 @@ static int ph_weights(pfslam_engine *e)
     k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(*e->cur_xc, e->sp, e->fit, e->w, e->n,
                                                                e->gidx0, n_sync, e->n_tiles, e->tiles_local, fuse,
                                                                e->n_global, e->prefix, e->res, 1, e->counters + 5);
+    if (e->laps_on) e->laps.mark(e->stream, kLapWeights);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+static const char *const kLapNames[kLapCount] = {"k_motion", "k_tile_prep", "k_score_tiled", "k_score_fast", "k_score_combine_rows",
+                                                 "k_weights_scan", "k_prefix", "k_map_free", "k_map_wall", "k_resample"};
+
+const char *pfslam_lap_name(int32_t id) { return id >= 0 && id < kLapCount ? kLapNames[id] : ""; }
+
+int pfslam_profile_laps(pfslam_engine *e, int32_t on)
+{
+    if (!e) return set_error(PFSLAM_ERR_ARG, "null engine");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (on && e->laps.ev.empty()) {
+        e->laps.ev.resize(16 * 1024);
+        e->laps.id.assign(e->laps.ev.size(), 0);
+        for (auto &ev : e->laps.ev) CUDA_TRY(cudaEventCreate(&ev));
+    }
+    e->laps_on = on != 0;
+    e->laps.n = 0;
+    return PFSLAM_OK;
+}
+
+int pfslam_profile_laps_read(pfslam_engine *e, float *ms_mean, int32_t *count)
+{
+    if (!e || !ms_mean || !count) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    double tot[kLapCount] = {};
+    for (int i = 0; i < kLapCount; i++) count[i] = 0;
+    for (int k = 1; k < e->laps.n; k++) {
+        const int id = e->laps.id[k];
+        if (id < 0) continue;                       // a step's start marker
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e->laps.ev[k - 1], e->laps.ev[k]));
+        tot[id] += ms; count[id]++;
+    }
+    for (int i = 0; i < kLapCount; i++) ms_mean[i] = count[i] ? (float)(tot[i] / count[i]) : 0.f;
+    e->laps.n = 0;
     return PFSLAM_OK;
 }
 
@@ -673,20 +735,30 @@ static int launch_prefix(pfslam_engine *e)
     const int nt = e->n_tiles * e->n_ranks;
     k_prefix<<<1, 1024, sizeof(float) * 2 * nt, e->stream>>>(*e->cur_xc, e->sp, e->n_tiles, e->n_global, e->prefix, e->res,
                                                              e->cfg.path == PFSLAM_PATH_KD ? 0 : 1);
+    if (e->laps_on) e->laps.mark(e->stream, kLapPrefix);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
 }
 
-static int launch_map(pfslam_engine *e)
+static int clear_map_masks(pfslam_engine *e, cudaStream_t st)
+{
+    CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, st));
+    return PFSLAM_OK;
+}
+
+// pose_from_ext: robotPos = the best particle's pose read from the exchanged extrema instead of the frame
+// result -- lets the map update run next to the weight / resample kernels (it needs nothing else from them)
+static int launch_map(pfslam_engine *e, cudaStream_t st, int pose_from_ext)
 {
     const StepParams *scan = e->sp;
-    CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, e->stream));
-    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, e->stream));
-    k_map_free<<<e->cfg.n_beams, 128, 0, e->stream>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
-                                                      e->counters);
-    k_map_wall<<<ceil_div(e->cfg.n_beams, 128), 128, 0, e->stream>>>(e->grid, e->geom, e->res, scan, e->angle,
-                                                                     e->cfg.n_beams, e->wall_bits, e->counters);
+    k_map_free<<<e->cfg.n_beams, 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
+                                               e->counters, *e->cur_xc, pose_from_ext);
+    if (e->laps_on) e->laps.mark(st, kLapMapFree);
+    k_map_wall<<<ceil_div(e->cfg.n_beams, 128), 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle,
+                                                              e->cfg.n_beams, e->wall_bits, e->counters, *e->cur_xc, pose_from_ext);
+    if (e->laps_on) e->laps.mark(st, kLapMapWall);
     e->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
@@ -701,7 +773,8 @@ static int ph_map(pfslam_engine *e, const float *scan_dev)
     int rc = push_params(e, scan_dev ? scan_dev : e->scan, e->cur.frame);
     if (rc) return rc;
     if ((rc = launch_prefix(e))) return rc;
-    return launch_map(e);
+    if ((rc = clear_map_masks(e, e->stream))) return rc;
+    return launch_map(e, e->stream, 0);
 }
 
 int pfslam_phase_map(pfslam_engine *e, const float *scan_dev)
@@ -716,6 +789,7 @@ static int ph_resample(pfslam_engine *e, int32_t frame)
     { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
     k_resample<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(*e->cur_xc, e->res, e->prefix, e->n_tiles, e->n, e->n_global,
                                                            e->gidx0, e->sp, e->x, e->y, e->th, e->w);
+    if (e->laps_on) e->laps.mark(e->stream, kLapResample);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
@@ -851,11 +925,30 @@ static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
 static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
 {
     int rc;
+    if (e->laps_on) e->laps.mark(e->stream, kLapStart);
     if ((rc = ph_motion(e, frame))) return rc;
+    if (!(e->overlap && !e->laps_on)) {
+        if ((rc = ph_score(e, scan_dev))) return rc;
+        if ((rc = ph_weights(e))) return rc;
+        if ((rc = ph_map(e, scan_dev))) return rc;
+        return ph_resample(e, frame);
+    }
+    // Two branches after the scores are in: {weights + tile scans, prefix / Neff, resample} on the main
+    // stream and {mask clears, free-cell and wall-cell map update} on the auxiliary one.  The map update
+    // needs only robotPos (the best particle's pose, taken from the extrema), the resample never reads the
+    // map, so the reference's order measurement -> map -> resample is preserved in effect.
+    CUDA_TRY(cudaEventRecord(e->ev_fork[1], e->stream));
+    CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork[1], 0));
+    if ((rc = clear_map_masks(e, e->aux))) return rc;      // off the critical path: overlaps the scoring
     if ((rc = ph_score(e, scan_dev))) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_fork[2], e->stream));
+    CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork[2], 0));
+    if ((rc = launch_map(e, e->aux, 1))) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_join[1], e->aux));
     if ((rc = ph_weights(e))) return rc;
-    if ((rc = ph_map(e, scan_dev))) return rc;
+    if ((rc = launch_prefix(e))) return rc;
     if ((rc = ph_resample(e, frame))) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[1], 0));
     return PFSLAM_OK;
 }
 
@@ -907,7 +1000,7 @@ int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
     e->seq++;
     if (e->cfg.path == PFSLAM_PATH_KD) return kd_step(e, scan_dev, frame);
     const float *scan = scan_dev ? scan_dev : e->scan;
-    if (e->use_graph && !e->prof_on && !e->graph_failed) {
+    if (e->use_graph && !e->prof_on && !e->laps_on && !e->graph_failed) {
         if (!e->graph_exec && build_graph(e) != 0) e->graph_failed = true;
         if (e->graph_exec) {
             StepParams *slot = nullptr;
@@ -981,7 +1074,9 @@ int pfslam_update_grid(pfslam_engine *e, const float *scan_host, const float pos
     e->h_res->pose[0] = pose[0]; e->h_res->pose[1] = pose[1]; e->h_res->pose[2] = pose[2];
     CUDA_TRY(cudaMemcpyAsync(e->res, e->h_res, sizeof(FrameResult), cudaMemcpyHostToDevice, e->stream));
     if ((rc = push_params(e, e->scan, e->cur.frame))) return rc;
-    if ((rc = launch_map(e))) return rc;
+    e->cur_xc = &e->xc_host;
+    if ((rc = clear_map_masks(e, e->stream))) return rc;
+    if ((rc = launch_map(e, e->stream, 0))) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PFSLAM_OK;
 }

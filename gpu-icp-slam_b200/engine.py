@@ -22,6 +22,7 @@ SCORE_EXACT, SCORE_FILTERED, SCORE_TILED = 0, 1, 2
 QUIRK_Q1 = 1
 QUIRKS_REFERENCE = QUIRK_Q1
 IPC_HANDLE_BYTES = 64
+LAP_COUNT = 10
 BUF_EXTREMA_LOCAL, BUF_EXTREMA_ALL, BUF_TILES_LOCAL, BUF_TILES_ALL, BUF_POSE_LOCAL, BUF_POSE_ALL, BUF_SCAN = range(7)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -105,6 +106,9 @@ _SIGS = {
     "pfslam_profile_score": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pfslam_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "pfslam_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "pfslam_profile_laps": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pfslam_profile_laps_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "pfslam_lap_name": (C.c_char_p, [C.c_int32]),
     "pfslam_debug_trig": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
@@ -321,6 +325,15 @@ class ParticleFilter:
         ms, n = C.c_float(), C.c_int32()
         self._check(self._lib.pfslam_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def profile_laps(self, on=True):
+        self._check(self._lib.pfslam_profile_laps(self._h, 1 if on else 0))
+
+    def profile_laps_read(self):
+        """{kernel name: (mean ms, launches)} of the serialised steps since profile_laps(True)"""
+        ms, cnt = (C.c_float * LAP_COUNT)(), (C.c_int32 * LAP_COUNT)()
+        self._check(self._lib.pfslam_profile_laps_read(self._h, ms, cnt))
+        return {self._lib.pfslam_lap_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(LAP_COUNT) if cnt[i]}
 
     def update_grid(self, scan, pose):
         """PFUpdateMap alone (src/kernel.cu:551) for an explicit robot pose."""

@@ -180,6 +180,14 @@ int  pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase);
 int  pfslam_profile_enable(pfslam_engine *e, int32_t on);
 int  pfslam_profile_read(pfslam_engine *e, float *ms_kernel_mean, int32_t *n_launches);
 
+/* per-kernel breakdown: while on, single-GPU grid steps run as plain, serialised launches (no graph, no
+ * side-by-side branches) with a CUDA event after every kernel; _read synchronises and returns, per lap id
+ * 0..PFSLAM_LAP_COUNT-1 (pfslam_lap_name gives the kernel), the mean duration in ms and the launch count */
+#define PFSLAM_LAP_COUNT 10
+int  pfslam_profile_laps(pfslam_engine *e, int32_t on);
+int  pfslam_profile_laps_read(pfslam_engine *e, float ms_mean[PFSLAM_LAP_COUNT], int32_t count[PFSLAM_LAP_COUNT]);
+const char *pfslam_lap_name(int32_t id);
+
 /* test hook: libdevice cosf/sinf of n host floats evaluated on the device (the functions the
  * reference's kernels call, kernel.cu:185-186); used to validate the oracle's emulation */
 int  pfslam_debug_trig(int32_t device, const float *x_host, int64_t n, float *cos_out, float *sin_out);

@@ -141,7 +141,13 @@ def test_free_running_against_reference_cuda_path(t3, scans):
         gm = pf.get_grid().reshape(-1)
         a, b = gr != -100, gm != -100
         iou = (a & b).sum() / float((a | b).sum())
-        occ_a, occ_b = gr > 0, gm > 0
-        occ_iou = (occ_a & occ_b).sum() / float(max((occ_a | occ_b).sum(), 1))
+        # walls are one cell thick and the two trajectories differ by a few cells (the reference's resample
+        # is racy, so its run is not even repeatable): compare the occupied cells with a 3-cell tolerance
+        from scipy.ndimage import binary_dilation
+        occ_a, occ_b = (gr > 0).reshape(1600, 1600), (gm > 0).reshape(1600, 1600)
+        k = np.ones((7, 7), bool)
+        near_ab = (occ_a & binary_dilation(occ_b, k)).sum() / float(max(occ_a.sum(), 1))
+        near_ba = (occ_b & binary_dilation(occ_a, k)).sum() / float(max(occ_b.sum(), 1))
     assert max(d) < 0.08, "trajectories drift apart: %g m" % max(d)
-    assert iou > 0.97 and occ_iou > 0.6, (iou, occ_iou)
+    assert occ_a.sum() > 200 and occ_b.sum() > 200
+    assert iou > 0.97 and near_ab > 0.9 and near_ba > 0.9, (iou, near_ab, near_ba)
