@@ -70,12 +70,12 @@ __device__ __forceinline__ float order_float(int k)
 }
 
 // Also reduces the post-noise pose bounds of the cloud (ordered-int min/max of x, y, theta) into
-// bounds[6] for the tiled scorer's window placement, and writes the pre-resample snapshot the
+// bounds[6] for the tiled scorer's window placement, zeroes the scorer's accumulator row, and writes the pre-resample snapshot the
 // resampler gathers from -- `snap` [parity][x | y | theta], null when a host all-gathers it.
 __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
          const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds,
-         float *__restrict__ snap, long long snap_stride, int parity_mask)
+         float *__restrict__ snap, long long snap_stride, int parity_mask, int *__restrict__ acc_row)
 {
     __shared__ int s_b[6];
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
@@ -90,6 +90,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
         float nt = pf_normal(st, 0.01f);
         const float vx = __fadd_rn(x[i], nx), vy = __fadd_rn(y[i], ny), vt = __fadd_rn(th[i], nt);
         x[i] = vx; y[i] = vy; th[i] = vt;
+        acc_row[i] = 0;                        // the tiled scorer adds into it (pf_score_tiled.cuh)
         if (snap) {
             float *sn = snap + (long long)(sp->seq & parity_mask) * snap_stride;
             sn[i] = vx; sn[n + i] = vy; sn[2 * n + i] = vt;
@@ -513,6 +514,15 @@ __device__ __forceinline__ void map_pose(const FrameResult *__restrict__ res, co
     }
 }
 
+// One warp that waits for every rank's flag of `kind`: heads a graph branch that consumes exchanged data
+// but does not follow a kernel that has already waited (the map branch).  A single spinning warp, so
+// that waiting never occupies the SMs the other shards' kernels may need.
+__global__ void k_xc_wait(const Xchg xc, const StepParams *__restrict__ sp, int kind, FrameResult *__restrict__ res)
+{
+    const bool ok = xc_wait_warp(xc, kind, sp->seq);
+    if (!ok && threadIdx.x == 0) res->xchg_timeout = 1;
+}
+
 __global__ void __launch_bounds__(128)
 k_map_free(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle,
@@ -522,10 +532,6 @@ k_map_free(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
     if (threadIdx.x == 0) s_cnt = 0;
-    if (pose_from_ext && xc.parity_mask && threadIdx.x < 32) {   // this branch does not follow k_weights_scan's wait
-        const bool ok = xc_wait_warp(xc, kXcExt, sp->seq);
-        if (!ok && blockIdx.x == 0 && threadIdx.x == 0) res->xchg_timeout = 1;
-    }
     __syncthreads();
     float pose[3];
     map_pose(res, xc, sp->seq, pose_from_ext, pose);

@@ -35,8 +35,7 @@ constexpr int kMaxChunks = 2 * kMaxGroups;  // each group gets up to two windows
 constexpr int kTiledThreads = 256;
 constexpr int kTiledPPT = 4;                // particles per thread
 constexpr int kTiledGroup = kTiledThreads * kTiledPPT;
-constexpr int kTiledY = 6;                  // chunk-interleaved blocks per particle group (grid.y)
-constexpr int kTiledQueueCap = 2048;
+constexpr int kTiledQueueCap = 1024;        // (particle, window) records with at least one uncertain beam, per group share
 constexpr float kMagicT = 8388608.0f;       // 2^23
 constexpr int kFracT = 16;
 constexpr float kGuardT = 64.0f;            // units of 2^-16 cell; band test = bits 7..15 zero (error bound 38)
@@ -48,6 +47,7 @@ struct TiledWork {
     int n_chunks, pad0, pad1, pad2;
     TileChunk chunk[kMaxChunks];
     int order[kMaxChunks];                     // non-empty window slots, in beam order
+    int cum[kMaxChunks + 1];                   // beams before order[i] (cum[n_chunks] = all tiled beams): work partition
     float4 tconst[kMaxChunks * kChunkBeams];   // {-Bx, Ay, Ax, By} in 2^-16-cell units (two FFMA2 operand pairs)
     int tbeam[kMaxChunks * kChunkBeams];       // original beam index
     int bounds[8];                             // cloud bounds as ordered ints: xmin,xmax,ymin,ymax,tmin,tmax
@@ -61,7 +61,7 @@ __global__ void k_bounds_reset(TiledWork *__restrict__ tw)
 // pose bounds of the local particle cloud (min/max of x, y, theta)
 __global__ void __launch_bounds__(256)
 k_cloud_bounds(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
-               TiledWork *__restrict__ tw)
+               TiledWork *__restrict__ tw, int *__restrict__ acc_row)
 {
     __shared__ int s_b[6];
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
@@ -69,6 +69,7 @@ k_cloud_bounds(const float *__restrict__ x, const float *__restrict__ y, const f
     int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int k0 = float_order(x[i]), k1 = float_order(y[i]), k2 = float_order(th[i]);
+        acc_row[i] = 0;                        // k_motion's other job when it did not run this frame
         lo[0] = min(lo[0], k0); hi[0] = max(hi[0], k0);
         lo[1] = min(lo[1], k1); hi[1] = max(hi[1], k1);
         lo[2] = min(lo[2], k2); hi[2] = max(hi[2], k2);
@@ -264,15 +265,25 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     __syncthreads();
     // the score kernel walks the non-empty windows only: compact their slots (beam order kept)
     if (warp == 0) {
-        int base_m = 0;
+        int base_m = 0, run = 0;
         for (int s0 = 0; s0 < 2 * n_groups; s0 += 32) {
             const int sl = s0 + lane;
-            const bool ne = sl < 2 * n_groups && s_cnt2[sl] > 0;
+            const int cv = sl < 2 * n_groups ? s_cnt2[sl] : 0;
+            const bool ne = cv > 0;
             const unsigned bm = __ballot_sync(0xffffffffu, ne);
-            if (ne) tw->order[base_m + __popc(bm & ((1u << lane) - 1))] = sl;
+            int inc = cv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            if (ne) {
+                const int pos = base_m + __popc(bm & ((1u << lane) - 1));
+                tw->order[pos] = sl;
+                tw->cum[pos] = run + inc - cv;
+            }
             base_m += __popc(bm);
+            run += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (lane == 0) {
+            tw->cum[base_m] = run;
             tw->n_chunks = base_m; wk->nf = s_nwide; wk->ns = s_nslow;
             // consumed: reset the cloud bounds for the next frame's k_motion
             for (int c = 0; c < 3; c++) { tw->bounds[2 * c] = 0x7fffffff; tw->bounds[2 * c + 1] = (int)0x80000000; }
@@ -324,41 +335,63 @@ struct TiledSmem {
     alignas(128) int8_t stage[kTileBytes];
     alignas(16) int8_t skew[kSkewBytes];
     alignas(16) float4 cst[2][kChunkBeams];
-    int beam[2][kChunkBeams];
-    unsigned queue[kTiledQueueCap];
+    uint2 queue[kTiledQueueCap];              // {particle << 8 | window slot, mask of uncertain beams}
     int acc[kTiledGroup];
     alignas(8) uint64_t bar;
     int qn;
+    int item0, item1;
 };
 
-// Tiled scoring: block = 256 threads x 4 particles = 1024 particles; blockIdx.y interleaves the
-// frame's chunks.  partial row blockIdx.y gets this block's per-particle sums.
-__global__ void __launch_bounds__(kTiledThreads)
+// Tiled scoring.  Work item = (group of 1024 particles, window); the items of a frame, in group-major
+// order and weighted by their beam counts, are cut into gridDim.x equal shares -- one per resident block
+// (grid = SMs x blocks/SM, a single full wave), so every SM carries the same load whatever the number
+// of windows.  block = 256 threads x 4 particles.  A block's share spans at most a few particle
+// groups; per group it keeps the sums in registers and adds them to acc_row[] (zeroed by k_motion) with
+// one atomic per particle.  Uncertain pairs are queued in shared memory across windows and re-evaluated
+// exactly once per group, so a window costs two block barriers (re-layout in, re-layout out).
+__global__ void __launch_bounds__(kTiledThreads, 3)
 k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
               const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
               const StepParams *__restrict__ sp, const float *__restrict__ angle,
-              const TiledWork *__restrict__ tw, int *__restrict__ partial, int *__restrict__ counters)
+              const TiledWork *__restrict__ tw, int *__restrict__ acc_row, int *__restrict__ counters)
 {
     const float *__restrict__ scan = sp->scan;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
     const int tid = threadIdx.x;
-    const int p0 = blockIdx.x * kTiledGroup + tid;
     const int n_chunks = tw->n_chunks;
-    const int c_first = blockIdx.y;
 
     if (tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.qn = 0;
+        // this block's share [item0, item1): items whose first beam-unit falls into its slice of the
+        // (groups x tiled beams) work line
+        int i0 = 0, i1 = 0;
+        const int bt = n_chunks > 0 ? tw->cum[n_chunks] : 0;
+        if (bt > 0) {
+            const int n_groups = (n + kTiledGroup - 1) / kTiledGroup;
+            const long long total = (long long)n_groups * bt;
+            const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+            for (int e = 0; e < 2; e++) {
+                const long long u = e ? hi : lo;
+                const int gq = (int)(u / bt), rem = (int)(u - (long long)gq * bt);
+                int a = 0, b = n_chunks;                         // first c with cum[c] >= rem
+                while (a < b) { const int mid = (a + b) >> 1; if (tw->cum[mid] < rem) a = mid + 1; else b = mid; }
+                (e ? i1 : i0) = gq * n_chunks + a;
+            }
+        }
+        sm.item0 = i0; sm.item1 = i1;
     }
 #pragma unroll
     for (int k = 0; k < kTiledPPT; k++) sm.acc[tid + k * kTiledThreads] = 0;
     __syncthreads();
+    const int item0 = sm.item0, item1 = sm.item1;
+    if (item0 >= item1) return;
     // prologue: the first window of this block in flight
-    if (tid == 0 && c_first < n_chunks) {
+    if (tid == 0) {
         mbar_expect_tx(&sm.bar, kTileBytes);
-        const int sl = tw->order[c_first];
+        const int sl = tw->order[item0 % n_chunks];
         tma_load_2d(sm.stage, &tmap, tw->chunk[sl].y0, tw->chunk[sl].x0, &sm.bar);
     }
 
@@ -370,27 +403,58 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
     float px[kTiledPPT], py[kTiledPPT];
     float2 cc[kTiledPPT], ss[kTiledPPT];
     int acc[kTiledPPT];
-#pragma unroll
-    for (int k = 0; k < kTiledPPT; k++) {
-        // lanes past the end take a copy of the last particle (results discarded), so every
-        // evaluation stays inside the staged window
-        const int p = min(p0 + k * kTiledThreads, n - 1);
-        px[k] = x[p]; py[k] = y[p];
-        const float a = th[p];
-        float sn, cs;
-        sincosf(a, &sn, &cs);
-        cc[k] = make_float2(cs, cs); ss[k] = make_float2(sn, sn);
-        acc[k] = 0;
-    }
+    int grp = -1;
 
-    int it = 0;
-    for (int ci = c_first; ci < n_chunks; ci += kTiledY, it++) {
-        const int s = it & 1;
+    // add this group's sums (registers + exact re-evaluations) to acc_row[] and reset them
+    auto flush = [&]() {
+        __syncthreads();                       // every warp has queued its uncertain pairs of this group
+        const int qn = min(sm.qn, kTiledQueueCap);
+        for (int qi = tid; qi < qn; qi += kTiledThreads) {
+            const uint2 e = sm.queue[qi];
+            const int pl = (int)(e.x >> 8), c = (int)(e.x & 0xffu);
+            const int p = grp * kTiledGroup + pl;
+            const float qx = x[p], qy = y[p], qt = th[p];
+            int v = 0;
+            for (unsigned m = e.y; m; m &= m - 1) {
+                const int j = tw->tbeam[c * kChunkBeams + __ffs(m) - 1];
+                v += eval_exact(grid, g, c0x, c0y, qx, qy, qt, angle[j], scan[j]);
+            }
+            if (v) atomicAdd(&sm.acc[pl], v);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTiledPPT; k++) {
+            const int pl = tid + k * kTiledThreads, p = grp * kTiledGroup + pl;
+            const int v = acc[k] + sm.acc[pl];
+            if (p < n && v) atomicAdd(&acc_row[p], v);
+            sm.acc[pl] = 0;
+        }
+        if (tid == 0) { if (sm.qn) atomicAdd(&counters[2], sm.qn); sm.qn = 0; }
+    };
+
+    for (int it = item0; it < item1; it++) {
+        const int li = it - item0, s = li & 1;
+        const int gi = it / n_chunks, ci = it - gi * n_chunks;
+        if (gi != grp) {
+            if (grp >= 0) flush();
+            grp = gi;
+#pragma unroll
+            for (int k = 0; k < kTiledPPT; k++) {
+                // lanes past the end take a copy of the last particle (results discarded), so every
+                // evaluation stays inside the staged window
+                const int p = min(grp * kTiledGroup + tid + k * kTiledThreads, n - 1);
+                px[k] = x[p]; py[k] = y[p];
+                float sn, cs;
+                sincosf(th[p], &sn, &cs);
+                cc[k] = make_float2(cs, cs); ss[k] = make_float2(sn, sn);
+                acc[k] = 0;
+            }
+        }
         const int c = tw->order[ci];
         const TileChunk tc = tw->chunk[c];
         if (tid < kChunkBeams) {
+            // constants of this window's beams; .w of a dead slot is never read (cnt bounds the loop)
             sm.cst[s][tid] = tid < tc.count ? tw->tconst[c * kChunkBeams + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
-            sm.beam[s][tid] = tw->tbeam[c * kChunkBeams + tid];
         }
         // window-relative fixed-point offsets of this thread's particles
         float2 P[kTiledPPT];
@@ -399,7 +463,8 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         for (int k = 0; k < kTiledPPT; k++)
             P[k] = make_float2(__fmaf_rn(__fmaf_rn(px[k], irx, offx), unit, mconst),
                                __fmaf_rn(__fmaf_rn(py[k], iry, offy), unit, mconst));
-        mbar_wait(&sm.bar, it & 1);            // window landed in `stage`
+        mbar_wait(&sm.bar, li & 1);            // window landed in `stage`
+        __syncthreads();                       // every warp has left the previous window's gather loop
         {   // re-lay the dense 128x128 box out with pitch 260 (+1 for columns >= 64)
             const int r = tid >> 1, h = tid & 1;
             const uint4 *src = reinterpret_cast<const uint4 *>(sm.stage + r * kTileX + h * 64);
@@ -418,12 +483,10 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             }
         }
         __syncthreads();                       // skewed window + constants visible; `stage` is free again
-        if (tid == 0) {
-            if (ci + kTiledY < n_chunks) {     // next window streams in while this one is scored
-                const int cn = tw->order[ci + kTiledY];
-                mbar_expect_tx(&sm.bar, kTileBytes);
-                tma_load_2d(sm.stage, &tmap, tw->chunk[cn].y0, tw->chunk[cn].x0, &sm.bar);
-            }
+        if (tid == 0 && it + 1 < item1) {      // next window streams in while this one is scored
+            const int cn = tw->order[(it + 1) % n_chunks];
+            mbar_expect_tx(&sm.bar, kTileBytes);
+            tma_load_2d(sm.stage, &tmap, tw->chunk[cn].y0, tw->chunk[cn].x0, &sm.bar);
         }
         const int8_t *tile = sm.skew;
         unsigned um[kTiledPPT];
@@ -431,7 +494,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         for (int k = 0; k < kTiledPPT; k++) um[k] = 0u;
         const int cnt = tc.count;
         unsigned bit = 1u;
-        // Main loop, ~10 instructions per evaluation: 2 FFMA2, PRMT, LEA.HI, LDS.S8, 4 for the guard-band
+        // Main loop, ~10 instructions per evaluation: 2 FFMA2, PRMT, LEA.HI, LDS.S8, 3 for the guard-band
         // test, then either the add (certain) or the beam's bit in the particle's mask (uncertain).
 #pragma unroll 4
         for (int b = 0; b < cnt; b++) {
@@ -444,50 +507,35 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 const uint32_t idx = prmt(bx, by, 0xBB26u);
                 const int v = (int)tile[idx + (idx >> 6)];
                 asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                    "and.b32 t, %2, 0xff80;\n\t"
-                    "setp.eq.u32 p, t, 0;\n\t"
-                    "and.b32 t, %3, 0xff80;\n\t"
-                    "setp.eq.or.u32 p, t, 0, p;\n\t"
+                    "mul.lo.u32 t, %2, 65536;\n\t"            // low 16 bits to the top: IMAD.SHL, off the ALU pipe
+                    "setp.lt.u32 p, t, 0x800000;\n\t"         // bits 7..15 == 0  <=>  (b << 16) < (128 << 16)
+                    "mul.lo.u32 t, %3, 65536;\n\t"
+                    "setp.lt.or.u32 p, t, 0x800000, p;\n\t"
                     "@p or.b32 %0, %0, %4;\n\t"
                     "@!p add.s32 %1, %1, %5;\n\t}"
                     : "+r"(um[k]), "+r"(acc[k]) : "r"(bx), "r"(by), "r"(bit), "r"(v));
             }
             bit <<= 1;
         }
-        // uncertain pairs (not added above): queue them for exact evaluation
+        // uncertain pairs (not added above): one record per (particle, window) for the group's exact pass
 #pragma unroll
         for (int k = 0; k < kTiledPPT; k++) {
-            unsigned m = (p0 + k * kTiledThreads < n) ? um[k] : 0u;
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
+            const int pl = tid + k * kTiledThreads;
+            const unsigned m0 = (grp * kTiledGroup + pl < n) ? um[k] : 0u;
+            if (m0) {
                 const int qi = atomicAdd(&sm.qn, 1);
-                if (qi < kTiledQueueCap) sm.queue[qi] = ((unsigned)(tid + k * kTiledThreads) << 8) | (unsigned)b;
+                if (qi < kTiledQueueCap) sm.queue[qi] = make_uint2(((unsigned)pl << 8) | (unsigned)c, m0);
                 else {
-                    const int j = sm.beam[s][b];
-                    acc[k] += eval_exact(grid, g, c0x, c0y, px[k], py[k], th[p0 + k * kTiledThreads], angle[j], scan[j]);
+                    const float qt = th[grp * kTiledGroup + pl];
+                    for (unsigned m = m0; m; m &= m - 1) {
+                        const int j = tw->tbeam[c * kChunkBeams + __ffs(m) - 1];
+                        acc[k] += eval_exact(grid, g, c0x, c0y, px[k], py[k], qt, angle[j], scan[j]);
+                    }
                 }
             }
         }
-        __syncthreads();                       // all reads of the window done; queue complete
-        const int qn = min(sm.qn, kTiledQueueCap);
-        for (int qi = tid; qi < qn; qi += kTiledThreads) {
-            const unsigned e = sm.queue[qi];
-            const int pl = (int)(e >> 8), b = (int)(e & 0xffu);
-            const int p = blockIdx.x * kTiledGroup + pl;
-            const int j = sm.beam[s][b];
-            const int v = eval_exact(grid, g, c0x, c0y, x[p], y[p], th[p], angle[j], scan[j]);
-            if (v) atomicAdd(&sm.acc[pl], v);
-        }
-        __syncthreads();
-        if (tid == 0) { if (sm.qn) atomicAdd(&counters[2], sm.qn); sm.qn = 0; }
     }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kTiledPPT; k++) {
-        const int p = p0 + k * kTiledThreads;
-        if (p < n) partial[(size_t)blockIdx.y * n + p] = acc[k] + sm.acc[tid + k * kTiledThreads];
-    }
+    flush();
 }
 
 // fit[p] = sum of n_rows partial rows; per-256-particle min / max-key partials
@@ -577,11 +625,16 @@ static int make_grid_tensor_map(CUtensorMap *out, const int8_t *grid, int map_w,
     return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-inline int score_tiled_rows() { return kTiledY + kFastSlices + 1; }   // tiled rows, wide-beam rows, slow-beam row
+inline int score_tiled_rows() { return 1 + kFastSlices + 1; }   // tiled accumulator row, wide-beam rows, slow-beam row
 
-static int score_tiled_setup()
+// returns the grid size of k_score_tiled = SMs x resident blocks per SM (one full wave), or -1
+static int score_tiled_setup(int device)
 {
-    return cudaFuncSetAttribute(k_score_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem)) == cudaSuccess ? 0 : -1;
+    if (cudaFuncSetAttribute(k_score_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem)) != cudaSuccess) return -1;
+    int per_sm = 0, n_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_tiled, kTiledThreads, sizeof(TiledSmem)) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    return per_sm > 0 && n_sm > 0 ? per_sm * n_sm : -1;
 }
 
 // returns the number of kernels launched, or -1.  partial: score_tiled_rows()*n ints.
@@ -592,7 +645,7 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                               const float *th, int n, int gidx0, const StepParams *scan, const float *angle, int n_beams,
                               int *fit, int *blk_min, long long *blk_maxkey, Extrema *ext_local,
                               ScoreFilteredWork *wk, TiledWork *tw, const double2 *angle_cs, bool bounds_valid,
-                              int *partial, int *counters, const Xchg &xc, cudaStream_t stream,
+                              int *partial, int *counters, const Xchg &xc, int tiled_grid, cudaStream_t stream,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                               cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                               LapRec *laps = nullptr)
@@ -600,20 +653,21 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
     int nl = 4;
     if (!bounds_valid) {   // poses were not produced by k_motion this frame (test hooks): recompute
         k_bounds_reset<<<1, 32, 0, stream>>>(tw);
-        k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw);
+        k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw, partial);
         nl += 2;
     }
     k_tile_prep<<<1, 1024, 0, stream>>>(scan, angle, angle_cs, n_beams, g, wk, tw);
     if (laps) laps->mark(stream, kLapTilePrep);
     if (aux) { cudaEventRecord(ev_fork, stream); cudaStreamWaitEvent(aux, ev_fork, 0); }
-    dim3 gt((n + kTiledGroup - 1) / kTiledGroup, kTiledY);
+    // one full wave; small filters get fewer blocks (an item is the smallest share)
+    const int gt = min(tiled_grid, ((n + kTiledGroup - 1) / kTiledGroup) * kMaxChunks);
     if (ev0) cudaEventRecord(ev0, stream);
     k_score_tiled<<<gt, kTiledThreads, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
     if (laps) laps->mark(stream, kLapScoreTiled);
     dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);          // last row = slow beams
     k_score_fast<<<gf, kFastThreads, 0, aux ? aux : stream>>>(grid, g, x, y, th, n, scan, angle, n_beams, wk,
-                                                              partial + (size_t)kTiledY * n, counters);
+                                                              partial + (size_t)n, counters);
     if (laps) laps->mark(stream, kLapScoreFast);
     if (aux) { cudaEventRecord(ev_join, aux); cudaStreamWaitEvent(stream, ev_join, 0); }
     const int nblk = (n + 255) / 256;

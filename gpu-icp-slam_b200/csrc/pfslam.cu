@@ -74,6 +74,7 @@ struct pfslam_engine {
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
+    int tiled_grid = 0;            // k_score_tiled grid: SMs x resident blocks per SM
     // pinned host staging
     float *h_scan = nullptr;
     FrameResult *h_res = nullptr;
@@ -333,7 +334,7 @@ static int preload_kernels()
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
     PF_PRELOAD(k_score_kd); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
     PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
-    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn);
+    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait);
 #undef PF_PRELOAD
     return PFSLAM_OK;
 }
@@ -402,7 +403,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
         if (!fixed_ok) e->score_mode = PFSLAM_SCORE_EXACT;
         if (e->score_mode == PFSLAM_SCORE_TILED) {
             if (cfg->n_beams > kMaxGroups * kChunkBeams || make_grid_tensor_map(&e->tmap, e->grid, e->geom.w, e->geom.h) != 0 ||
-                score_tiled_setup() != 0)
+                (e->tiled_grid = score_tiled_setup(cfg->device)) <= 0)
                 e->score_mode = PFSLAM_SCORE_FILTERED;
         }
     }
@@ -553,7 +554,7 @@ static int ph_motion(pfslam_engine *e, int32_t frame)
     const Xchg &xc = *e->cur_xc;
     // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
     k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
-                                                         xc.snap, xc.snap_stride, xc.parity_mask);
+                                                         xc.snap, xc.snap_stride, xc.parity_mask, e->score_partial);
     if (e->laps_on) e->laps.mark(e->stream, kLapMotion);
     e->bounds_valid = true;
     e->launches++;
@@ -588,7 +589,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
     } else if (e->score_mode == PFSLAM_SCORE_TILED) {
         int nl = score_tiled_launch(e->tmap, e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                     e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
-                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->stream, ev0, ev1,
+                                    e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->tiled_grid, e->stream, ev0, ev1,
                                     use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr);
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
@@ -753,6 +754,10 @@ static int clear_map_masks(pfslam_engine *e, cudaStream_t st)
 static int launch_map(pfslam_engine *e, cudaStream_t st, int pose_from_ext)
 {
     const StepParams *scan = e->sp;
+    if (pose_from_ext && e->cur_xc->parity_mask) {      // this branch does not follow k_weights_scan's wait
+        k_xc_wait<<<1, 32, 0, st>>>(*e->cur_xc, e->sp, kXcExt, e->res);
+        e->launches++;
+    }
     k_map_free<<<e->cfg.n_beams, 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
                                                e->counters, *e->cur_xc, pose_from_ext);
     if (e->laps_on) e->laps.mark(st, kLapMapFree);
