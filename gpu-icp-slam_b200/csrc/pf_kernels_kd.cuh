@@ -86,6 +86,73 @@ __device__ __forceinline__ int kd_nn(const KdNode *__restrict__ tree, float qx, 
     return bestIdx;
 }
 
+// ---- search shadow of the tree ---------------------------------------------------------------------------
+// The scoring walk touches a node per tree level per (particle, beam), and the reference's insert-grown
+// trees are deep (measured on train_lidar0: mean depth 20, max ~100 at 6 k nodes).  For the planar
+// clouds this engine builds (every z == 0, queries with z == 0) the walk needs only x, y, the split axis
+// and the two links of a node, so the scorer walks a 16-byte shadow {x, y, left | axis << 30, right}
+// (one LDG.128 per visit) rebuilt from the 32-byte nodes after every topology change; parent and weight
+// of the winning node come from the full node.  Arithmetic is unchanged: with dz == 0,
+// fma(dz, dz, fma(dx, dx, dy*dy)) == fma(dx, dx, dy*dy) exactly, and the z-level test `qz < node.z` is
+// false (always right).  Trees with any z != 0 (only reachable through pfslam_set_kd) use kd_nn<>.
+struct KdSearch { float x, y; int lr0, right; };
+constexpr int kKdNoLeft = 0x3fffffff;
+
+__global__ void __launch_bounds__(256)
+k_kd_shadow(const KdNode *__restrict__ tree, const KdState *__restrict__ ks, KdSearch *__restrict__ out, int cap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap || i >= ks->size) return;
+    const KdNode n = kd_load_cg(tree, i);
+    KdSearch s;
+    s.x = n.x; s.y = n.y;
+    s.lr0 = (n.left & kKdNoLeft) | (n.axis << 30);
+    s.right = n.right;
+    reinterpret_cast<int4 *>(out)[i] = make_int4(__float_as_int(s.x), __float_as_int(s.y), s.lr0, s.right);
+}
+
+__device__ __forceinline__ int kd_nn_flat(const KdSearch *__restrict__ sh, const KdNode *__restrict__ tree, float qx, float qy)
+{
+    float best2, bestDist;
+    int bestIdx = 0, head = 0;
+    {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(sh));
+        const float dx = __fsub_rn(__int_as_float(v.x), qx), dy = __fsub_rn(__int_as_float(v.y), qy);
+        best2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+        bestDist = __fsqrt_rn(best2);
+    }
+    bool explored = false;
+    for (;;) {
+        while (head >= 0) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(sh) + head);
+            const float nx = __int_as_float(v.x), ny = __int_as_float(v.y);
+            const float dx = __fsub_rn(nx, qx), dy = __fsub_rn(ny, qy);
+            const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            if (d2 < best2) {
+                const float d = __fsqrt_rn(d2);
+                if (d < bestDist) { bestDist = d; best2 = d2; bestIdx = head; explored = false; }
+            }
+            const unsigned axis = (unsigned)v.z >> 30;
+            const bool branch = axis == 0u ? qx < nx : axis == 1u ? qy < ny : false;
+            head = branch ? (v.z << 2) >> 2 : v.w;
+        }
+        if (explored) break;
+        const int bestParent = __ldg(&tree[bestIdx].parent);
+        if (bestParent < 0) break;
+        const int4 p = __ldg(reinterpret_cast<const int4 *>(sh) + bestParent);
+        const unsigned axis = (unsigned)p.z >> 30;
+        const float px = __int_as_float(p.x), py = __int_as_float(p.y);
+        bool branch = false; float hd = 0.0f;
+        if (axis == 0u) { branch = qx < px; hd = fabsf(__fsub_rn(qx, px)); }
+        if (axis == 1u) { branch = qy < py; hd = fabsf(__fsub_rn(qy, py)); }
+        if (axis == 2u) { branch = false; hd = 0.0f; }          // |qz - p.z| with both 0
+        if (!(hd < bestDist)) break;
+        head = !branch ? (p.z << 2) >> 2 : p.w;
+        explored = true;
+    }
+    return bestIdx;
+}
+
 // kd NN lookup alone (the "kd-tree NN lookup" entry point): one thread per query
 __global__ void k_kd_nn(const KdNode *__restrict__ tree, const KdState *__restrict__ ks, const float *__restrict__ q3,
                         int n, int *__restrict__ out)
@@ -100,8 +167,9 @@ __global__ void k_kd_nn(const KdNode *__restrict__ tree, const KdState *__restri
 // block = 8 warps, lane = particle, warp w takes beams w, w+8, ...  (Interleaving 4 walks per thread
 // for memory-level parallelism was measured SLOWER, 5.5 vs 3.7 ms: the kernel is bound by divergent
 // instruction issue, not by load latency.)
+template <bool kFlat>
 __global__ void __launch_bounds__(256)
-k_score_kd(const KdNode *__restrict__ tree, const float *__restrict__ x, const float *__restrict__ y,
+k_score_kd(const KdNode *__restrict__ tree, const KdSearch *__restrict__ sh, const float *__restrict__ x, const float *__restrict__ y,
            const float *__restrict__ th, int n, int gidx0, const StepParams *__restrict__ sp,
            const float *__restrict__ angle, int n_beams, int *__restrict__ fit, int *__restrict__ blk_min,
            long long *__restrict__ blk_maxkey)
@@ -118,7 +186,8 @@ k_score_kd(const KdNode *__restrict__ tree, const float *__restrict__ x, const f
             const float r = __ldg(&scan[j]);
             const float wx = __fmul_rn(r, cosf(rot)), wy = __fmul_rn(r, sinf(rot));
             if (fabsf(wx) < kLidarRange && fabsf(wy) < kLidarRange) {
-                const int k = kd_nn<false>(tree, __fadd_rn(wx, px), __fadd_rn(wy, py), 0.0f);
+                const int k = kFlat ? kd_nn_flat(sh, tree, __fadd_rn(wx, px), __fadd_rn(wy, py))
+                                    : kd_nn<false>(tree, __fadd_rn(wx, px), __fadd_rn(wy, py), 0.0f);
                 acc += (int)__ldg(&tree[k].w);
             }
         }

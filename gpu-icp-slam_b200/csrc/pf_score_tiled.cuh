@@ -40,6 +40,7 @@ constexpr float kMagicT = 8388608.0f;       // 2^23
 constexpr int kFracT = 16;
 constexpr float kGuardT = 64.0f;            // units of 2^-16 cell; band test = bits 7..15 zero (error bound 38)
 constexpr int kBoxMargin = 2;               // cells added around the conservative hit box
+constexpr int kWindowCostBeams = 8;         // fixed cost of a window (TMA wait, re-layout, two barriers) in beam units
 
 struct TileChunk { int x0, y0, count, pad; };
 
@@ -47,7 +48,7 @@ struct TiledWork {
     int n_chunks, pad0, pad1, pad2;
     TileChunk chunk[kMaxChunks];
     int order[kMaxChunks];                     // non-empty window slots, in beam order
-    int cum[kMaxChunks + 1];                   // beams before order[i] (cum[n_chunks] = all tiled beams): work partition
+    int cum[kMaxChunks + 1];                   // work (beams + per-window cost) before order[i]; cum[n_chunks] = total
     float4 tconst[kMaxChunks * kChunkBeams];   // {-Bx, Ay, Ax, By} in 2^-16-cell units (two FFMA2 operand pairs)
     int tbeam[kMaxChunks * kChunkBeams];       // original beam index
     int bounds[8];                             // cloud bounds as ordered ints: xmin,xmax,ymin,ymax,tmin,tmax
@@ -271,13 +272,14 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             const int cv = sl < 2 * n_groups ? s_cnt2[sl] : 0;
             const bool ne = cv > 0;
             const unsigned bm = __ballot_sync(0xffffffffu, ne);
-            int inc = cv;
+            int inc = ne ? cv + kWindowCostBeams : 0;         // work weight of the window
+            const int wv = inc;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
             if (ne) {
                 const int pos = base_m + __popc(bm & ((1u << lane) - 1));
                 tw->order[pos] = sl;
-                tw->cum[pos] = run + inc - cv;
+                tw->cum[pos] = run + inc - wv;
             }
             base_m += __popc(bm);
             run += __shfl_sync(0xffffffffu, inc, 31);

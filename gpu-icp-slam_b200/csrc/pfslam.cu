@@ -81,6 +81,9 @@ struct pfslam_engine {
     long long launches = 0;
     // kd-tree point-cloud path
     KdNode *kd = nullptr; int kd_cap = 0;
+    KdSearch *kds = nullptr;               // 16-byte search shadow of kd (planar trees)
+    int kd_size_ub = 0;                    // host-side upper bound of the device tree size
+    bool kd_flat = true;                   // every node has z == 0 and a valid axis: the scorer walks the shadow
     KdState *ks = nullptr;
     int *bits_blk = nullptr; int n_bits_blk = 0;
     int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 4096;
@@ -192,7 +195,7 @@ int pfslam_destroy(pfslam_engine *e)
     if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
     cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->angle_cs); cudaFree(e->sp);
-    cudaFree(e->kd); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
+    cudaFree(e->kd); cudaFree(e->kds); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
     cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index);
     for (int r = 0; r < kMaxRanks; r++) if (e->peer_ipc[r] && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
     cudaFree(e->xreg);
@@ -286,6 +289,7 @@ static int engine_alloc(pfslam_engine *e)
     if (e->cfg.path == PFSLAM_PATH_KD) {
         e->kd_cap = e->cfg.kd_capacity > 0 ? e->cfg.kd_capacity : (1 << 21);
         CUDA_TRY(cudaMalloc(&e->kd, sizeof(KdNode) * (size_t)e->kd_cap));
+        CUDA_TRY(cudaMalloc(&e->kds, sizeof(KdSearch) * (size_t)e->kd_cap));
         CUDA_TRY(cudaMalloc(&e->ks, sizeof(KdState)));
         CUDA_TRY(cudaMemsetAsync(e->ks, 0, sizeof(KdState), e->stream));
         e->n_bits_blk = ceil_div((int)(e->bits_bytes / 4), kBitsBlockWords);
@@ -332,7 +336,7 @@ static int preload_kernels()
     PF_PRELOAD(k_beam_prep); PF_PRELOAD(k_score_tiled); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
     PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
-    PF_PRELOAD(k_score_kd); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
+    PF_PRELOAD(k_score_kd<true>); PF_PRELOAD(k_score_kd<false>); PF_PRELOAD(k_kd_shadow); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
     PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
     PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait);
 #undef PF_PRELOAD
@@ -836,6 +840,29 @@ static void kd_build(std::vector<KdPt> &pts, KdNode *list)
     kd_build_range(pts.data(), pts.data() + pts.size(), list, 0, -1);
 }
 
+// rebuild the scorer's search shadow after a topology change (first build, insert, rebalance, set_kd)
+static int kd_refresh_shadow(pfslam_engine *e, int n_nodes_hint)
+{
+    if (n_nodes_hint > 0) e->kd_size_ub = n_nodes_hint;
+    const int cover = std::min(e->kd_size_ub, e->kd_cap);
+    if (cover <= 0) return PFSLAM_OK;
+    k_kd_shadow<<<ceil_div(cover, 256), 256, 0, e->stream>>>(e->kd, e->ks, e->kds, e->kd_cap);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PFSLAM_OK;
+}
+
+static void launch_score_kd(pfslam_engine *e)
+{
+    if (e->kd_flat)
+        k_score_kd<true><<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->kds, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
+                                                                   e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+    else
+        k_score_kd<false><<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->kds, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
+                                                                    e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+    e->launches++;
+}
+
 // frame % 100 == 5 (kernel.cu:1707-1711): device tree -> host rebuild -> device
 static int kd_balance(pfslam_engine *e)
 {
@@ -851,7 +878,7 @@ static int kd_balance(pfslam_engine *e)
     kd_build(pts, e->h_kd.data());
     CUDA_TRY(cudaMemcpyAsync(e->kd, e->h_kd.data(), sizeof(KdNode) * st.size, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    return PFSLAM_OK;
+    return kd_refresh_shadow(e, st.size);
 }
 
 // PFUpdateMapKD (kernel.cu:1406-1540)
@@ -885,12 +912,17 @@ static int kd_update_map(pfslam_engine *e)
             st.size = nW; st.n_ins = nW;
             CUDA_TRY(cudaMemcpy(e->ks, &st, sizeof st, cudaMemcpyHostToDevice));
             e->kd_empty = false;
+            int rc = kd_refresh_shadow(e, nW);
+            if (rc) return rc;
         }
     } else {
         k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 0, e->kd_pts, e->kd_nn_idx);
         k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 1, e->kd_pts, e->kd_nn_idx);
         k_kd_insert<<<1, 1024, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, e->kd_cap, e->kd_pts, e->kd_nn_idx, e->kd_ins_index);
         e->launches += 3;
+        // the tree size lives on the device: cover an upper bound (at most pc_cap inserts per frame)
+        e->kd_size_ub = std::min(e->kd_cap, e->kd_size_ub + e->pc_cap);
+        { int rc = kd_refresh_shadow(e, 0); if (rc) return rc; }
     }
     k_kd_finish<<<1, 1, 0, e->stream>>>(e->res, e->ks, e->counters);
     e->launches += 1;
@@ -911,12 +943,11 @@ static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
     if ((rc = ph_motion(e, frame))) return rc;
     const bool prof = e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2;
     if (prof) cudaEventRecord(e->prof_ev[2 * e->prof_n], e->stream);
-    k_score_kd<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
-                                                         e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+    launch_score_kd(e);
     if (prof) { cudaEventRecord(e->prof_ev[2 * e->prof_n + 1], e->stream); e->prof_n++; }
     k_extrema<<<1, 1024, 0, e->stream>>>(e->blk_min, e->blk_maxkey, ceil_div(e->n, 32), e->x, e->y, e->th, e->gidx0,
                                          e->ext_local, *e->cur_xc, e->sp);
-    e->launches += 2;
+    e->launches += 1;
     e->bounds_valid = false;
     if ((rc = ph_weights(e))) return rc;
     k_icp<<<1, 1024, sizeof(float) * 5 * e->cfg.n_beams, e->stream>>>(e->kd, *e->cur_xc, e->sp, e->angle,
@@ -1094,9 +1125,7 @@ int pfslam_score_particles(pfslam_engine *e, const float *scan_host, int32_t *fi
     if (e->cfg.path == PFSLAM_PATH_KD) {
         if (e->kd_empty) return set_error(PFSLAM_ERR_STATE, "no kd tree yet");
         if ((rc = push_params(e, e->scan, e->cur.frame))) return rc;
-        k_score_kd<<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
-                                                             e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
-        e->launches++;
+        launch_score_kd(e);
     } else if ((rc = pfslam_phase_score(e, nullptr))) return rc;
     CUDA_TRY(cudaMemcpyAsync(fit_out, e->fit, sizeof(int) * e->n, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -1225,7 +1254,12 @@ int pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes)
     CUDA_TRY(cudaMemcpyAsync(e->ks, &st, sizeof st, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->kd_empty = false;
-    return PFSLAM_OK;
+    // the scorer's shadow walk assumes a planar tree: z == 0 everywhere, axes in {0, 1, 2}
+    const KdNode *nd = static_cast<const KdNode *>(nodes_in);
+    e->kd_flat = true;
+    for (int i = 0; i < n_nodes && e->kd_flat; i++)
+        e->kd_flat = nd[i].z == 0.0f && nd[i].axis >= 0 && nd[i].axis <= 2;
+    return kd_refresh_shadow(e, n_nodes);
 }
 
 int64_t pfslam_launch_count(pfslam_engine *e) { return e ? e->launches : 0; }
