@@ -75,7 +75,7 @@ __device__ __forceinline__ float order_float(int k)
 __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
          const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds,
-         float *__restrict__ snap, long long snap_stride, int parity_mask, int *__restrict__ acc_row)
+         float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row)
 {
     __shared__ int s_b[6];
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
@@ -93,7 +93,8 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
         acc_row[i] = 0;                        // the tiled scorer adds into it (pf_score_tiled.cuh)
         if (snap) {
             float *sn = snap + (long long)(sp->seq & parity_mask) * snap_stride;
-            sn[i] = vx; sn[n + i] = vy; sn[2 * n + i] = vt;
+            if (snap_aos) reinterpret_cast<float4 *>(sn)[i] = make_float4(vx, vy, vt, 0.0f);
+            else { sn[i] = vx; sn[n + i] = vy; sn[2 * n + i] = vt; }
         }
         lo[0] = hi[0] = float_order(vx); lo[1] = hi[1] = float_order(vy); lo[2] = hi[2] = float_order(vt);
     }
@@ -461,7 +462,12 @@ k_resample(const Xchg xc, const FrameResult *__restrict__ res, const float *__re
     }
     const int r = src / n_local, l = src - r * n_local;
     const float *pp = xc.pose_src[r] + (long long)(seq & xc.parity_mask) * xc.snap_stride;
-    x[i] = pp[l]; y[i] = pp[n_local + l]; th[i] = pp[2 * n_local + l];
+    if (xc.snap_aos) {
+        const float4 v = reinterpret_cast<const float4 *>(pp)[l];
+        x[i] = v.x; y[i] = v.y; th[i] = v.z;
+    } else {
+        x[i] = pp[l]; y[i] = pp[n_local + l]; th[i] = pp[2 * n_local + l];
+    }
     w[i] = 1.0f;
 }
 

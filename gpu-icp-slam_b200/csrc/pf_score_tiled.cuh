@@ -27,7 +27,7 @@ namespace pf {
 
 constexpr int kTileX = 128;                 // window rows (x cells) and usable columns (y cells)
 constexpr int kTileBytes = kTileX * kTileX; // dense TMA box: 128 (y, contiguous) x 128 (x) bytes
-constexpr int kSkewPitch = 260;             // bank-conflict-free row pitch of the gather copy
+constexpr int kSkewPitch = 272;             // row pitch of the gather copy (bank = 4 x + y/4 mod 32, see TiledSmem)
 constexpr int kSkewBytes = kTileX * kSkewPitch + 16;
 constexpr int kChunkBeams = 32;
 constexpr int kMaxGroups = 64;              // groups of 32 consecutive fast beams (2048 beams)
@@ -329,18 +329,35 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 
 // Shared-memory gather layout.  The PRMT offset is idx = x*256 + y; a row pitch of 256 B would put
 // every row in the same banks (measured: ~7 wavefronts per LDS).  One LEA.HI turns it into
-//     addr = idx + (idx >> 6) = x*260 + y + (y >> 6)
-// i.e. pitch 260 (bank = x + y/4 mod 32: a compact 2-D footprint is conflict free) with columns
-// 64..127 displaced by one byte.  The TMA box lands densely in `stage`; the block re-lays it out
-// into `skew` once per chunk (~40 instructions per thread against ~1200 in the beam loop).
+//     addr = idx + (idx >> 4) = x*272 + y + (y >> 4)
+// i.e. pitch 272 with every 16-byte group of a row displaced by one more byte (group q starts at 17 q).
+// bank = (4 x + y/4) mod 32: the 32 particles of a warp hit a footprint of a few rows x a few words,
+// which this lattice keeps apart (simulated on the fixture's clouds: 1.2 wavefronts per gather against
+// 2.2 for pitch 260 / shift 6, 2.0 for pitch 288 / shift 3).  The TMA box lands densely in `stage`;
+// the block re-lays it out into `skew` once per window: a thread moves half a row (4 groups) with one
+// PRMT per destination word (bytes 4m+b of the half row come from source byte 4m+b - q, q = (4m+b)/17).
+__host__ __device__ constexpr uint32_t skew_selector(int m)
+{
+    uint32_t sel = 0;
+    for (int b = 0; b < 4; b++) {
+        const int k = 4 * m + b, q = k / 17;
+        int n = 4 + b - q;                    // byte of the pair (w[m-1], w[m]); gap bytes take any valid source
+        if (m == 16 && n > 3) n = 3;          // there is no w[16]: the last byte is a gap
+        sel |= (uint32_t)n << (4 * b);
+    }
+    return sel;
+}
+
 struct TiledSmem {
     alignas(128) int8_t stage[kTileBytes];
     alignas(16) int8_t skew[kSkewBytes];
     alignas(16) float4 cst[2][kChunkBeams];
     uint2 queue[kTiledQueueCap];              // {particle << 8 | window slot, mask of uncertain beams}
     int acc[kTiledGroup];
+    alignas(16) int4 win[kMaxChunks];         // {x0, y0, beam count, window slot} of order[i]: the frame's window table
+    int cum[kMaxChunks + 1];
     alignas(8) uint64_t bar;
-    int qn;
+    int qn, npairs;
     int item0, item1;
 };
 
@@ -363,14 +380,29 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
     const int tid = threadIdx.x;
     const int n_chunks = tw->n_chunks;
 
+    // the frame's window table and work prefix into shared memory (one parallel round of global loads;
+    // everything per-window afterwards is an LDS)
+    for (int i = tid; i <= n_chunks; i += kTiledThreads) {
+        sm.cum[i] = tw->cum[i];
+        if (i < n_chunks) {
+            const int sl = tw->order[i];
+            const TileChunk tc = tw->chunk[sl];
+            sm.win[i] = make_int4(tc.x0, tc.y0, tc.count, sl);
+        }
+    }
     if (tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sm.qn = 0;
-        // this block's share [item0, item1): items whose first beam-unit falls into its slice of the
-        // (groups x tiled beams) work line
+        sm.qn = 0; sm.npairs = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kTiledPPT; k++) sm.acc[tid + k * kTiledThreads] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        // this block's share [item0, item1): items whose first work unit falls into its slice of the
+        // (groups x frame work) line
         int i0 = 0, i1 = 0;
-        const int bt = n_chunks > 0 ? tw->cum[n_chunks] : 0;
+        const int bt = n_chunks > 0 ? sm.cum[n_chunks] : 0;
         if (bt > 0) {
             const int n_groups = (n + kTiledGroup - 1) / kTiledGroup;
             const long long total = (long long)n_groups * bt;
@@ -379,22 +411,24 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 const long long u = e ? hi : lo;
                 const int gq = (int)(u / bt), rem = (int)(u - (long long)gq * bt);
                 int a = 0, b = n_chunks;                         // first c with cum[c] >= rem
-                while (a < b) { const int mid = (a + b) >> 1; if (tw->cum[mid] < rem) a = mid + 1; else b = mid; }
+                while (a < b) { const int mid = (a + b) >> 1; if (sm.cum[mid] < rem) a = mid + 1; else b = mid; }
                 (e ? i1 : i0) = gq * n_chunks + a;
             }
         }
         sm.item0 = i0; sm.item1 = i1;
     }
-#pragma unroll
-    for (int k = 0; k < kTiledPPT; k++) sm.acc[tid + k * kTiledThreads] = 0;
     __syncthreads();
     const int item0 = sm.item0, item1 = sm.item1;
     if (item0 >= item1) return;
-    // prologue: the first window of this block in flight
+    // prologue: the first window of this block in flight, and its beam constants
     if (tid == 0) {
         mbar_expect_tx(&sm.bar, kTileBytes);
-        const int sl = tw->order[item0 % n_chunks];
-        tma_load_2d(sm.stage, &tmap, tw->chunk[sl].y0, tw->chunk[sl].x0, &sm.bar);
+        const int4 w0 = sm.win[item0 % n_chunks];
+        tma_load_2d(sm.stage, &tmap, w0.y, w0.x, &sm.bar);
+    }
+    if (tid < kChunkBeams) {
+        const int4 w0 = sm.win[item0 % n_chunks];
+        sm.cst[0][tid] = tid < w0.z ? tw->tconst[w0.w * kChunkBeams + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
     const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
@@ -406,23 +440,28 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
     float2 cc[kTiledPPT], ss[kTiledPPT];
     int acc[kTiledPPT];
     int grp = -1;
+    int n_inline = 0;                          // pairs this thread re-evaluated inline (queue overflow)
 
     // add this group's sums (registers + exact re-evaluations) to acc_row[] and reset them
     auto flush = [&]() {
         __syncthreads();                       // every warp has queued its uncertain pairs of this group
         const int qn = min(sm.qn, kTiledQueueCap);
+        int np = n_inline;
+        n_inline = 0;
         for (int qi = tid; qi < qn; qi += kTiledThreads) {
             const uint2 e = sm.queue[qi];
             const int pl = (int)(e.x >> 8), c = (int)(e.x & 0xffu);
             const int p = grp * kTiledGroup + pl;
             const float qx = x[p], qy = y[p], qt = th[p];
             int v = 0;
+            np += __popc(e.y);
             for (unsigned m = e.y; m; m &= m - 1) {
                 const int j = tw->tbeam[c * kChunkBeams + __ffs(m) - 1];
                 v += eval_exact(grid, g, c0x, c0y, qx, qy, qt, angle[j], scan[j]);
             }
             if (v) atomicAdd(&sm.acc[pl], v);
         }
+        if (np) atomicAdd(&sm.npairs, np);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kTiledPPT; k++) {
@@ -431,7 +470,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             if (p < n && v) atomicAdd(&acc_row[p], v);
             sm.acc[pl] = 0;
         }
-        if (tid == 0) { if (sm.qn) atomicAdd(&counters[2], sm.qn); sm.qn = 0; }
+        if (tid == 0) { if (sm.npairs) atomicAdd(&counters[2], sm.npairs); sm.qn = 0; sm.npairs = 0; }
     };
 
     for (int it = item0; it < item1; it++) {
@@ -452,11 +491,15 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 acc[k] = 0;
             }
         }
-        const int c = tw->order[ci];
-        const TileChunk tc = tw->chunk[c];
-        if (tid < kChunkBeams) {
-            // constants of this window's beams; .w of a dead slot is never read (cnt bounds the loop)
-            sm.cst[s][tid] = tid < tc.count ? tw->tconst[c * kChunkBeams + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int4 wi = sm.win[ci];
+        const int c = wi.w;
+        TileChunk tc; tc.x0 = wi.x; tc.y0 = wi.y; tc.count = wi.z; tc.pad = 0;
+        // the next window's beam constants start their trip from L2 now and land in the other buffer after
+        // this window's gather loop (nobody reads that buffer until the next barrier pair)
+        float4 cst_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < kChunkBeams && it + 1 < item1) {
+            const int4 wn = sm.win[(it + 1) % n_chunks];
+            if (tid < wn.z) cst_next = tw->tconst[wn.w * kChunkBeams + tid];
         }
         // window-relative fixed-point offsets of this thread's particles
         float2 P[kTiledPPT];
@@ -467,28 +510,23 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                                __fmaf_rn(__fmaf_rn(py[k], iry, offy), unit, mconst));
         mbar_wait(&sm.bar, li & 1);            // window landed in `stage`
         __syncthreads();                       // every warp has left the previous window's gather loop
-        {   // re-lay the dense 128x128 box out with pitch 260 (+1 for columns >= 64)
+        {   // re-lay the dense 128x128 box out: pitch 272, 16-byte group q of a row at byte 17 q
             const int r = tid >> 1, h = tid & 1;
             const uint4 *src = reinterpret_cast<const uint4 *>(sm.stage + r * kTileX + h * 64);
-            uint32_t w[16];
+            uint32_t w[17];
 #pragma unroll
             for (int i = 0; i < 4; i++) { const uint4 v = src[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-            uint32_t *dst = reinterpret_cast<uint32_t *>(sm.skew + r * kSkewPitch + h * 64);
-            if (h == 0) {
+            w[16] = 0u;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sm.skew + r * kSkewPitch + h * 68);
+            dst[0] = w[0];
 #pragma unroll
-                for (int i = 0; i < 16; i++) dst[i] = w[i];
-            } else {
-                dst[0] = w[0] << 8;
-#pragma unroll
-                for (int i = 1; i < 16; i++) dst[i] = __funnelshift_l(w[i - 1], w[i], 8);
-                dst[16] = w[15] >> 24;
-            }
+            for (int m = 1; m < 17; m++) dst[m] = prmt(w[m - 1], w[m], skew_selector(m));
         }
         __syncthreads();                       // skewed window + constants visible; `stage` is free again
         if (tid == 0 && it + 1 < item1) {      // next window streams in while this one is scored
-            const int cn = tw->order[(it + 1) % n_chunks];
+            const int4 wn = sm.win[(it + 1) % n_chunks];
             mbar_expect_tx(&sm.bar, kTileBytes);
-            tma_load_2d(sm.stage, &tmap, tw->chunk[cn].y0, tw->chunk[cn].x0, &sm.bar);
+            tma_load_2d(sm.stage, &tmap, wn.y, wn.x, &sm.bar);
         }
         const int8_t *tile = sm.skew;
         unsigned um[kTiledPPT];
@@ -496,7 +534,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         for (int k = 0; k < kTiledPPT; k++) um[k] = 0u;
         const int cnt = tc.count;
         unsigned bit = 1u;
-        // Main loop, ~10 instructions per evaluation: 2 FFMA2, PRMT, LEA.HI, LDS.S8, 3 for the guard-band
+        // Main loop, ~12 instructions per evaluation: 2 FFMA2, PRMT, LEA.HI, LDS.S8, 4 for the guard-band
         // test, then either the add (certain) or the beam's bit in the particle's mask (uncertain).
 #pragma unroll 4
         for (int b = 0; b < cnt; b++) {
@@ -507,7 +545,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 const float2 t2 = __ffma2_rn(hi, cc[k], __ffma2_rn(lo, ss[k], P[k]));
                 const uint32_t bx = __float_as_uint(t2.x), by = __float_as_uint(t2.y);
                 const uint32_t idx = prmt(bx, by, 0xBB26u);
-                const int v = (int)tile[idx + (idx >> 6)];
+                const int v = (int)tile[idx + (idx >> 4)];
                 asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
                     "mul.lo.u32 t, %2, 65536;\n\t"            // low 16 bits to the top: IMAD.SHL, off the ALU pipe
                     "setp.lt.u32 p, t, 0x800000;\n\t"         // bits 7..15 == 0  <=>  (b << 16) < (128 << 16)
@@ -519,20 +557,40 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             }
             bit <<= 1;
         }
-        // uncertain pairs (not added above): one record per (particle, window) for the group's exact pass
+        if (tid < kChunkBeams) sm.cst[s ^ 1][tid] = cst_next;
+        // uncertain pairs (not added above): one record per (particle, window) for the group's exact pass.
+        // One shared-memory atomic per warp: the lanes' record counts are prefix-summed with shuffles.
+        {
+            const int lane = tid & 31;
+            unsigned mk[kTiledPPT];
+            int cntm = 0;
 #pragma unroll
-        for (int k = 0; k < kTiledPPT; k++) {
-            const int pl = tid + k * kTiledThreads;
-            const unsigned m0 = (grp * kTiledGroup + pl < n) ? um[k] : 0u;
-            if (m0) {
-                const int qi = atomicAdd(&sm.qn, 1);
-                if (qi < kTiledQueueCap) sm.queue[qi] = make_uint2(((unsigned)pl << 8) | (unsigned)c, m0);
-                else {
-                    const float qt = th[grp * kTiledGroup + pl];
-                    for (unsigned m = m0; m; m &= m - 1) {
-                        const int j = tw->tbeam[c * kChunkBeams + __ffs(m) - 1];
-                        acc[k] += eval_exact(grid, g, c0x, c0y, px[k], py[k], qt, angle[j], scan[j]);
+            for (int k = 0; k < kTiledPPT; k++) {
+                mk[k] = (grp * kTiledGroup + tid + k * kTiledThreads < n) ? um[k] : 0u;
+                cntm += mk[k] ? 1 : 0;
+            }
+            if (__any_sync(0xffffffffu, cntm)) {
+                int inc = cntm;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&sm.qn, inc);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                int qi = base + inc - cntm;
+#pragma unroll
+                for (int k = 0; k < kTiledPPT; k++) {
+                    if (!mk[k]) continue;
+                    const int pl = tid + k * kTiledThreads;
+                    if (qi < kTiledQueueCap) sm.queue[qi] = make_uint2(((unsigned)pl << 8) | (unsigned)c, mk[k]);
+                    else {
+                        const float qt = th[grp * kTiledGroup + pl];
+                        n_inline += __popc(mk[k]);
+                        for (unsigned m = mk[k]; m; m &= m - 1) {
+                            const int j = tw->tbeam[c * kChunkBeams + __ffs(m) - 1];
+                            acc[k] += eval_exact(grid, g, c0x, c0y, px[k], py[k], qt, angle[j], scan[j]);
+                        }
                     }
+                    qi++;
                 }
             }
         }

@@ -41,11 +41,13 @@ struct Xchg {
     unsigned timeout_ms;          // bound on every flag wait
     long long tiles_block;        // floats per (parity, source rank) tiles block
     long long sum_off, lm_off;    // offsets of [tsum_w | tsum_w2] and lm[] inside a tiles block
-    long long snap_stride;        // floats between the two parities of a pose snapshot (3 n)
+    long long snap_stride;        // floats between the two parities of a pose snapshot
+    int snap_aos;                 // snapshot layout: 1 = float4 {x, y, theta, 0} per particle (one 16-byte gather,
+                                  // one NVLink transaction per pull), 0 = x[] | y[] | theta[] (what a host all-gathers)
     // this rank's view (own region when parity_mask, else the engine's local / host-gathered buffers)
     Extrema *ext_all;             // [parity][kMaxRanks]
     float   *tiles_all;           // [parity][n_ranks][tiles_block]
-    float   *snap;                // own pre-resample snapshot [parity][x | y | theta]; null: host gathers
+    float   *snap;                // own pre-resample snapshot [parity][...]; null: host gathers
     int     *flags;               // [kind][kMaxRanks] sequence numbers, written by the peers
     // every rank's region (peer memory) and the byte offsets of the parts inside a region
     unsigned char *peer[kMaxRanks];

@@ -242,7 +242,7 @@ static int engine_alloc(pfslam_engine *e)
         e->ext_all = e->ext_local;
         e->tiles_all = e->tiles_local;
     }
-    CUDA_TRY(cudaMalloc(&e->pose_all, sizeof(float) * 3 * (size_t)n * e->n_ranks));
+    CUDA_TRY(cudaMalloc(&e->pose_all, sizeof(float) * (e->n_ranks == 1 ? 4 : 3) * (size_t)n * e->n_ranks));
     CUDA_TRY(cudaMalloc(&e->prefix, sizeof(float) * ((size_t)e->n_tiles * e->n_ranks + 1)));
     {   // single GPU, or a host that runs its own collectives between the phases
         Xchg &h = e->xc_host;
@@ -250,6 +250,7 @@ static int engine_alloc(pfslam_engine *e)
         h.tiles_block = e->tiles_block; h.sum_off = 0; h.lm_off = 2ll * e->n_tiles; h.snap_stride = 0;
         h.ext_all = e->ext_all; h.tiles_all = e->tiles_all;
         h.snap = e->n_ranks == 1 ? e->pose_all : nullptr;
+        h.snap_aos = e->n_ranks == 1 ? 1 : 0;
         for (int r = 0; r < e->n_ranks && r < kMaxRanks; r++) h.pose_src[r] = e->pose_all + (size_t)r * 3 * n;
         e->cur_xc = &e->xc_host;
     }
@@ -261,14 +262,14 @@ static int engine_alloc(pfslam_engine *e)
         e->xoff_ext = up(sizeof(int) * 2 * kMaxRanks);
         e->xoff_tiles = up(e->xoff_ext + sizeof(Extrema) * 2 * kMaxRanks);
         e->xoff_snap = up(e->xoff_tiles + sizeof(float) * 2 * e->n_ranks * tb);
-        e->xreg_bytes = up(e->xoff_snap + sizeof(float) * 2 * 3 * (size_t)n);
+        e->xreg_bytes = up(e->xoff_snap + sizeof(float) * 2 * 4 * (size_t)n);
         CUDA_TRY(cudaMalloc(&e->xreg, e->xreg_bytes));
         CUDA_TRY(cudaMemsetAsync(e->xreg, 0, e->xreg_bytes, e->stream));
         Xchg &x = e->xc_p2p;
         x.n_ranks = e->n_ranks; x.rank = e->gidx0 / n; x.parity_mask = 1;
         const char *to = getenv("PFSLAM_PEER_TIMEOUT_MS");
         x.timeout_ms = to ? (unsigned)atoi(to) : 10000u;
-        x.tiles_block = (long long)tb; x.sum_off = n; x.lm_off = 0; x.snap_stride = 3ll * n;
+        x.tiles_block = (long long)tb; x.sum_off = n; x.lm_off = 0; x.snap_stride = 4ll * n; x.snap_aos = 1;
         x.ext_all = reinterpret_cast<Extrema *>(e->xreg + e->xoff_ext);
         x.tiles_all = reinterpret_cast<float *>(e->xreg + e->xoff_tiles);
         x.snap = reinterpret_cast<float *>(e->xreg + e->xoff_snap);
@@ -558,7 +559,7 @@ static int ph_motion(pfslam_engine *e, int32_t frame)
     const Xchg &xc = *e->cur_xc;
     // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
     k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
-                                                         xc.snap, xc.snap_stride, xc.parity_mask, e->score_partial);
+                                                         xc.snap, xc.snap_stride, xc.parity_mask, xc.snap_aos, e->score_partial);
     if (e->laps_on) e->laps.mark(e->stream, kLapMotion);
     e->bounds_valid = true;
     e->launches++;
