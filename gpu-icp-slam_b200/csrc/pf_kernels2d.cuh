@@ -357,22 +357,38 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
     }
     __syncthreads();
     if (!s_last) return;
+    // The last block to finish also does k_prefix's job when asked to (global tile prefix in tile order,
+    // Neff, resample decision, robotPos).  Sharded over peer memory it first raises this rank's tile
+    // flags, then waits for everybody's: one spinning block, and no separate kernel on the critical path.
     if (xc.parity_mask) {
         if (threadIdx.x == 0) { *done_counter = 0; xc_signal(xc, kXcTiles, seq); }
-        return;
+        if (!fuse_prefix) return;
+        if (threadIdx.x < 32) {
+            const bool ok = xc_wait_warp(xc, kXcTiles, seq);
+            if (!ok && threadIdx.x == 0) res->xchg_timeout = 1;
+        }
+        __syncthreads();
+    } else {
+        __threadfence();
     }
-    // single-GPU engines: the last block to finish also does k_prefix's job (global tile prefix in
-    // tile order, Neff, resample decision, robotPos)
-    __threadfence();
     __shared__ float s_t[2 * kFusedPrefixMaxTiles];
-    for (int t = threadIdx.x; t < 2 * n_tiles; t += blockDim.x) s_t[t] = __ldcg(&tiles_local[xc.sum_off + t]);
+    const int nt = xc.n_ranks * n_tiles;
+    {
+        const float *all = xc.parity_mask ? xc_tiles(xc, seq) : tiles_local;
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+            const int r = t / n_tiles, tl = t - r * n_tiles;
+            const float *blk = all + (long long)r * xc.tiles_block + xc.sum_off;
+            s_t[t] = __ldcg(&blk[tl]);
+            s_t[nt + t] = __ldcg(&blk[n_tiles + tl]);
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         float p = 0.0f, p2 = 0.0f;
         prefix[0] = 0.0f;
-        for (int t = 0; t < n_tiles; t++) {
+        for (int t = 0; t < nt; t++) {
             p = __fadd_rn(p, s_t[t]);
-            p2 = __fadd_rn(p2, s_t[n_tiles + t]);
+            p2 = __fadd_rn(p2, s_t[nt + t]);
             prefix[t + 1] = p;
         }
         const float neff = __fdiv_rn(__fmul_rn(p, p), p2);
@@ -380,7 +396,7 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
         res->sum_w = p; res->sum_w2 = p2; res->neff = neff;
         res->resampled = ((double)neff < 0.7 * (double)n_global) ? 1 : 0;
-        *done_counter = 0;
+        if (!xc.parity_mask) *done_counter = 0;
     }
 }
 

@@ -32,9 +32,7 @@ constexpr int kSkewBytes = kTileX * kSkewPitch + 16;
 constexpr int kChunkBeams = 32;
 constexpr int kMaxGroups = 64;              // groups of 32 consecutive fast beams (2048 beams)
 constexpr int kMaxChunks = 2 * kMaxGroups;  // each group gets up to two windows
-constexpr int kTiledThreads = 256;
-constexpr int kTiledPPT = 4;                // particles per thread
-constexpr int kTiledGroup = kTiledThreads * kTiledPPT;
+constexpr int kTiledGroup = 1024;           // particles per block: 256 threads x 4, or 512 threads x 2 (PFSLAM_TILED_THREADS)
 constexpr int kTiledQueueCap = 1024;        // (particle, window) records with at least one uncertain beam, per group share
 constexpr float kMagicT = 8388608.0f;       // 2^23
 constexpr int kFracT = 16;
@@ -368,7 +366,8 @@ struct TiledSmem {
 // groups; per group it keeps the sums in registers and adds them to acc_row[] (zeroed by k_motion) with
 // one atomic per particle.  Uncertain pairs are queued in shared memory across windows and re-evaluated
 // exactly once per group, so a window costs two block barriers (re-layout in, re-layout out).
-__global__ void __launch_bounds__(kTiledThreads, 3)
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, (PPT == 4 ? 3 : 2))
 k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
               const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
               const StepParams *__restrict__ sp, const float *__restrict__ angle,
@@ -382,7 +381,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
 
     // the frame's window table and work prefix into shared memory (one parallel round of global loads;
     // everything per-window afterwards is an LDS)
-    for (int i = tid; i <= n_chunks; i += kTiledThreads) {
+    for (int i = tid; i <= n_chunks; i += THREADS) {
         sm.cum[i] = tw->cum[i];
         if (i < n_chunks) {
             const int sl = tw->order[i];
@@ -396,7 +395,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         sm.qn = 0; sm.npairs = 0;
     }
 #pragma unroll
-    for (int k = 0; k < kTiledPPT; k++) sm.acc[tid + k * kTiledThreads] = 0;
+    for (int k = 0; k < PPT; k++) sm.acc[tid + k * THREADS] = 0;
     __syncthreads();
     if (tid == 0) {
         // this block's share [item0, item1): items whose first work unit falls into its slice of the
@@ -436,9 +435,9 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
     const float unit = (float)(1 << kFracT);
     const float irx = (float)(1.0 / (double)g.res_x), iry = (float)(1.0 / (double)g.res_y);
     const float mconst = kMagicT + 0.5f * unit + kGuardT;      // exact
-    float px[kTiledPPT], py[kTiledPPT];
-    float2 cc[kTiledPPT], ss[kTiledPPT];
-    int acc[kTiledPPT];
+    float px[PPT], py[PPT];
+    float2 cc[PPT], ss[PPT];
+    int acc[PPT];
     int grp = -1;
     int n_inline = 0;                          // pairs this thread re-evaluated inline (queue overflow)
 
@@ -448,7 +447,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         const int qn = min(sm.qn, kTiledQueueCap);
         int np = n_inline;
         n_inline = 0;
-        for (int qi = tid; qi < qn; qi += kTiledThreads) {
+        for (int qi = tid; qi < qn; qi += THREADS) {
             const uint2 e = sm.queue[qi];
             const int pl = (int)(e.x >> 8), c = (int)(e.x & 0xffu);
             const int p = grp * kTiledGroup + pl;
@@ -464,8 +463,8 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         if (np) atomicAdd(&sm.npairs, np);
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kTiledPPT; k++) {
-            const int pl = tid + k * kTiledThreads, p = grp * kTiledGroup + pl;
+        for (int k = 0; k < PPT; k++) {
+            const int pl = tid + k * THREADS, p = grp * kTiledGroup + pl;
             const int v = acc[k] + sm.acc[pl];
             if (p < n && v) atomicAdd(&acc_row[p], v);
             sm.acc[pl] = 0;
@@ -480,10 +479,10 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             if (grp >= 0) flush();
             grp = gi;
 #pragma unroll
-            for (int k = 0; k < kTiledPPT; k++) {
+            for (int k = 0; k < PPT; k++) {
                 // lanes past the end take a copy of the last particle (results discarded), so every
                 // evaluation stays inside the staged window
-                const int p = min(grp * kTiledGroup + tid + k * kTiledThreads, n - 1);
+                const int p = min(grp * kTiledGroup + tid + k * THREADS, n - 1);
                 px[k] = x[p]; py[k] = y[p];
                 float sn, cs;
                 sincosf(th[p], &sn, &cs);
@@ -502,15 +501,15 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             if (tid < wn.z) cst_next = tw->tconst[wn.w * kChunkBeams + tid];
         }
         // window-relative fixed-point offsets of this thread's particles
-        float2 P[kTiledPPT];
+        float2 P[PPT];
         const float offx = __fsub_rn(c0x, (float)tc.x0), offy = __fsub_rn(c0y, (float)tc.y0);
 #pragma unroll
-        for (int k = 0; k < kTiledPPT; k++)
+        for (int k = 0; k < PPT; k++)
             P[k] = make_float2(__fmaf_rn(__fmaf_rn(px[k], irx, offx), unit, mconst),
                                __fmaf_rn(__fmaf_rn(py[k], iry, offy), unit, mconst));
         mbar_wait(&sm.bar, li & 1);            // window landed in `stage`
         __syncthreads();                       // every warp has left the previous window's gather loop
-        {   // re-lay the dense 128x128 box out: pitch 272, 16-byte group q of a row at byte 17 q
+        if (tid < 2 * kTileX) {   // re-lay the dense 128x128 box out: pitch 272, 16-byte group q of a row at byte 17 q
             const int r = tid >> 1, h = tid & 1;
             const uint4 *src = reinterpret_cast<const uint4 *>(sm.stage + r * kTileX + h * 64);
             uint32_t w[17];
@@ -529,9 +528,9 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             tma_load_2d(sm.stage, &tmap, wn.y, wn.x, &sm.bar);
         }
         const int8_t *tile = sm.skew;
-        unsigned um[kTiledPPT];
+        unsigned um[PPT];
 #pragma unroll
-        for (int k = 0; k < kTiledPPT; k++) um[k] = 0u;
+        for (int k = 0; k < PPT; k++) um[k] = 0u;
         const int cnt = tc.count;
         unsigned bit = 1u;
         // Main loop, ~12 instructions per evaluation: 2 FFMA2, PRMT, LEA.HI, LDS.S8, 4 for the guard-band
@@ -541,7 +540,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             const float4 q = sm.cst[s][b];
             const float2 lo = make_float2(q.x, q.y), hi = make_float2(q.z, q.w);
 #pragma unroll
-            for (int k = 0; k < kTiledPPT; k++) {
+            for (int k = 0; k < PPT; k++) {
                 const float2 t2 = __ffma2_rn(hi, cc[k], __ffma2_rn(lo, ss[k], P[k]));
                 const uint32_t bx = __float_as_uint(t2.x), by = __float_as_uint(t2.y);
                 const uint32_t idx = prmt(bx, by, 0xBB26u);
@@ -562,11 +561,11 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         // One shared-memory atomic per warp: the lanes' record counts are prefix-summed with shuffles.
         {
             const int lane = tid & 31;
-            unsigned mk[kTiledPPT];
+            unsigned mk[PPT];
             int cntm = 0;
 #pragma unroll
-            for (int k = 0; k < kTiledPPT; k++) {
-                mk[k] = (grp * kTiledGroup + tid + k * kTiledThreads < n) ? um[k] : 0u;
+            for (int k = 0; k < PPT; k++) {
+                mk[k] = (grp * kTiledGroup + tid + k * THREADS < n) ? um[k] : 0u;
                 cntm += mk[k] ? 1 : 0;
             }
             if (__any_sync(0xffffffffu, cntm)) {
@@ -578,9 +577,9 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 base = __shfl_sync(0xffffffffu, base, 31);
                 int qi = base + inc - cntm;
 #pragma unroll
-                for (int k = 0; k < kTiledPPT; k++) {
+                for (int k = 0; k < PPT; k++) {
                     if (!mk[k]) continue;
-                    const int pl = tid + k * kTiledThreads;
+                    const int pl = tid + k * THREADS;
                     if (qi < kTiledQueueCap) sm.queue[qi] = make_uint2(((unsigned)pl << 8) | (unsigned)c, mk[k]);
                     else {
                         const float qt = th[grp * kTiledGroup + pl];
@@ -687,12 +686,25 @@ static int make_grid_tensor_map(CUtensorMap *out, const int8_t *grid, int map_w,
 
 inline int score_tiled_rows() { return 1 + kFastSlices + 1; }   // tiled accumulator row, wide-beam rows, slow-beam row
 
+// block shape of k_score_tiled: 256 threads x 4 particles (3 blocks / SM) or 512 x 2 (2 blocks / SM, more warps)
+static int tiled_threads()
+{
+    static int v = 0;
+    if (!v) { const char *e = getenv("PFSLAM_TILED_THREADS"); v = (e && atoi(e) == 512) ? 512 : 256; }
+    return v;
+}
+
 // returns the grid size of k_score_tiled = SMs x resident blocks per SM (one full wave), or -1
 static int score_tiled_setup(int device)
 {
-    if (cudaFuncSetAttribute(k_score_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem)) != cudaSuccess) return -1;
     int per_sm = 0, n_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_tiled, kTiledThreads, sizeof(TiledSmem)) != cudaSuccess) return -1;
+    if (tiled_threads() == 512) {
+        if (cudaFuncSetAttribute(k_score_tiled<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem)) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_tiled<512, 2>, 512, sizeof(TiledSmem)) != cudaSuccess) return -1;
+    } else {
+        if (cudaFuncSetAttribute(k_score_tiled<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem)) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_tiled<256, 4>, 256, sizeof(TiledSmem)) != cudaSuccess) return -1;
+    }
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
     return per_sm > 0 && n_sm > 0 ? per_sm * n_sm : -1;
 }
@@ -722,7 +734,10 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
     // one full wave; small filters get fewer blocks (an item is the smallest share)
     const int gt = min(tiled_grid, ((n + kTiledGroup - 1) / kTiledGroup) * kMaxChunks);
     if (ev0) cudaEventRecord(ev0, stream);
-    k_score_tiled<<<gt, kTiledThreads, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+    if (tiled_threads() == 512)
+        k_score_tiled<512, 2><<<gt, 512, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+    else
+        k_score_tiled<256, 4><<<gt, 256, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
     if (laps) laps->mark(stream, kLapScoreTiled);
     dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);          // last row = slow beams

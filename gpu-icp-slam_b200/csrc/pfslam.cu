@@ -334,7 +334,7 @@ static int preload_kernels()
     cudaFuncAttributes a;
 #define PF_PRELOAD(k) CUDA_TRY(cudaFuncGetAttributes(&a, k))
     PF_PRELOAD(k_motion); PF_PRELOAD(k_cloud_bounds); PF_PRELOAD(k_bounds_reset); PF_PRELOAD(k_tile_prep);
-    PF_PRELOAD(k_beam_prep); PF_PRELOAD(k_score_tiled); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
+    PF_PRELOAD(k_beam_prep); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<256, 4>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<512, 2>)); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
     PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
     PF_PRELOAD(k_score_kd<true>); PF_PRELOAD(k_score_kd<false>); PF_PRELOAD(k_kd_shadow); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
@@ -679,8 +679,10 @@ int pfslam_profile_score(pfslam_engine *e, float *ms_kernel, float *ms_phase)
 static int ph_weights(pfslam_engine *e)
 {
     const int n_sync = (e->cfg.quirks & PFSLAM_QUIRK_Q1_HALF_WEIGHT_SYNC) ? (e->n_global + 1) / 2 : e->n_global;
-    // single-GPU grid path: the prefix step rides in the same launch (the kd path needs ICP in between)
-    const int fuse = (e->n_ranks == 1 && e->cfg.path == PFSLAM_PATH_GRID2D && e->n_tiles <= kFusedPrefixMaxTiles) ? 1 : 0;
+    // grid path: the prefix step rides in the same launch (the kd path needs ICP in between, and a host that
+    // runs its own collectives needs the tiles gathered first)
+    const bool local_or_peer = e->n_ranks == 1 || e->cur_xc->parity_mask;
+    const int fuse = (local_or_peer && e->cfg.path == PFSLAM_PATH_GRID2D && e->n_tiles * e->n_ranks <= kFusedPrefixMaxTiles) ? 1 : 0;
     e->prefix_fused = fuse != 0;
     k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(*e->cur_xc, e->sp, e->fit, e->w, e->n,
                                                                e->gidx0, n_sync, e->n_tiles, e->tiles_local, fuse,
