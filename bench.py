@@ -102,6 +102,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def scorer_traffic():
+    """DRAM bytes per k_score_tiled launch (dram__bytes_read + dram__bytes_write) from the committed ncu
+    --set full capture (tools/ncu_summary.py writes the file); None when there is none"""
+    p = os.path.join(ROOT, "profiles", "score_tiled_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["traffic_bytes_per_launch"]), d.get("source", "")
+    except Exception:
+        return None, ""
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -347,6 +358,7 @@ def run_ours(args):
         if kd:   # one 32-B node per tree level per (particle, beam): N*B*32*ceil(log2 kdSize)
             alg_bytes = n * N_BEAMS * 32 * int(np.ceil(np.log2(max(r.kd_size, 2))))
         achieved = alg_bytes / (ker * 1e-3) / 1e9
+        traffic, traffic_src = (None, "") if kd else scorer_traffic()
         line = {
             "metric": METRIC + ("_kd" if kd else ""), "value": K / (dev_ms * 1e-3) * scale, "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -367,7 +379,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": 4 * N_BEAMS, "d2h_bytes_per_step": C.sizeof(g.FrameResult)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_score_kd" if kd else "k_score_tiled", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker, "kernel_launches_timed": n_prof,
                          "kernel_ms_isolated": float(np.mean([a for a, _ in iso_ms])),
                          "scoring_phase_ms_isolated": float(np.mean([b for _, b in iso_ms]))},
