@@ -50,6 +50,8 @@ struct TiledWork {
     float4 tconst[kMaxChunks * kChunkBeams];   // {-Bx, Ay, Ax, By} in 2^-16-cell units (two FFMA2 operand pairs)
     int tbeam[kMaxChunks * kChunkBeams];       // original beam index
     int bounds[8];                             // cloud bounds as ordered ints: xmin,xmax,ymin,ymax,tmin,tmax
+    int wide_run, slow_run;                    // running sizes of the wide / slow lists while k_tile_prep's warps append
+    int done;                                  // warps of k_tile_prep that have finished this frame
 };
 
 __global__ void k_bounds_reset(TiledWork *__restrict__ tw)
@@ -112,162 +114,138 @@ __global__ void k_init_beam_trig(const float *__restrict__ angle, int n_beams, d
     if (j < n_beams) { double a = (double)angle[j]; cs[j] = make_double2(cos(a), sin(a)); }
 }
 
-// Per-frame preparation (one block, 1024 threads, up to 2048 beams): classify every beam as
+// Per-frame preparation, one WARP per group of 32 consecutive beams (up to 64 groups = 2048 beams), no
+// block-wide step: classify every beam as
 //   slow  (outside the fast domain: r >= 20 m, sentinel, NaN)        -> wk->slow   (k_score_fast, exact row)
-//   tiled (conservative hit box fits its chunk's 128x128 window)    -> tw chunks  (k_score_tiled)
+//   tiled (conservative hit box fits its group's 128x128 window)    -> tw chunks  (k_score_tiled)
 //   wide  (fast domain, but does not fit)                           -> wk->fconst (k_score_fast)
-__global__ void __launch_bounds__(1024)
+// A group gets a window placed on all of its beams; the beams that do not fit get a second window of
+// their own; what still does not fit is "wide".  The last warp to finish compacts the non-empty windows
+// (order / cum) and the groups' wide and slow lists, and resets the cloud bounds for the next frame.
+constexpr int kPrepWarps = 8;
+__global__ void __launch_bounds__(kPrepWarps * 32)
 k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             const double2 *__restrict__ angle_cs, int n_beams, MapGeom g,
-            ScoreFilteredWork *__restrict__ wk, TiledWork *__restrict__ tw)
+            ScoreFilteredWork *__restrict__ wk, TiledWork *tw)
 {
     const float *__restrict__ scan = sp->scan;
-    __shared__ int s_scan[32];
-    __shared__ int4 s_box[2048];
-    __shared__ int s_j[2048];
-    __shared__ int s_nelig, s_nslow, s_nwide;
-    __shared__ int s_cnt2[kMaxChunks];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) { s_nwide = 0; }
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);       // beam group
+    const int n_groups = (n_beams + kChunkBeams - 1) / kChunkBeams;
+    if (c >= n_groups) return;
     const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
     const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
-    const double pxmin = (double)order_float(tw->bounds[0]), pxmax = (double)order_float(tw->bounds[1]);
-    const double pymin = (double)order_float(tw->bounds[2]), pymax = (double)order_float(tw->bounds[3]);
-    const double tmin = (double)order_float(tw->bounds[4]), tmax = (double)order_float(tw->bounds[5]);
+    const double pxmin = (double)order_float(__ldcg(&tw->bounds[0])), pxmax = (double)order_float(__ldcg(&tw->bounds[1]));
+    const double pymin = (double)order_float(__ldcg(&tw->bounds[2])), pymax = (double)order_float(__ldcg(&tw->bounds[3]));
+    const double tmin = (double)order_float(__ldcg(&tw->bounds[4])), tmax = (double)order_float(__ldcg(&tw->bounds[5]));
     // the fixed-point error bound assumes poses within kFastMaxPoseCells of the map centre
     const double lim_x = (double)kFastMaxPoseCells * (double)g.res_x, lim_y = (double)kFastMaxPoseCells * (double)g.res_y;
     const bool cloud_ok = pxmin <= pxmax && pymin <= pymax && tmin <= tmax &&
                           fabs(pxmin) < lim_x && fabs(pxmax) < lim_x && fabs(pymin) < lim_y && fabs(pymax) < lim_y &&
                           fabs(tmin) < 1e3 && fabs(tmax) < 1e3;
 
-    // ---- phase A: thread t owns beams 2t, 2t+1
-    bool elig[2], slow[2];
-    int4 box[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int j = 2 * t + k;
-        elig[k] = slow[k] = false;
-        box[k] = make_int4(0, 0, 0, 0);
-        if (j < n_beams) {
-            const float r = scan[j];
-            const double rx = (double)r / (double)g.res_x, ry = (double)r / (double)g.res_y;
-            const bool fast = fabs(rx) < (double)kFastMaxCells && fabs(ry) < (double)kFastMaxCells;
-            slow[k] = !fast;
-            if (fast) {
-                elig[k] = true;
-                if (cloud_ok) {
-                    float cmin, cmax, smin, smax;
-                    const float a = angle[j];
-                    // interval of rot = angle + theta over the cloud, padded for float rounding
-                    trig_range(a + (float)tmin - 4e-6f, a + (float)tmax + 4e-6f, cmin, cmax, smin, smax);
-                    const double xa = rx * (double)cmin, xb = rx * (double)cmax, ya = ry * (double)smin, yb = ry * (double)smax;
-                    const double vx0 = (double)c0x + pxmin / (double)g.res_x + fmin(xa, xb);
-                    const double vx1 = (double)c0x + pxmax / (double)g.res_x + fmax(xa, xb);
-                    const double vy0 = (double)c0y + pymin / (double)g.res_y + fmin(ya, yb);
-                    const double vy1 = (double)c0y + pymax / (double)g.res_y + fmax(ya, yb);
-                    box[k] = make_int4((int)floor(vx0) - kBoxMargin, (int)ceil(vx1) + kBoxMargin,
-                                       (int)floor(vy0) - kBoxMargin, (int)ceil(vy1) + kBoxMargin);
-                } else {
-                    box[k] = make_int4(-(1 << 20), 1 << 20, -(1 << 20), 1 << 20);   // never fits -> wide
-                }
-            }
-        }
-    }
-    // dense indices (beam order) by a block scan of per-thread counts
-    const int ce = (int)elig[0] + (int)elig[1], cs = (int)slow[0] + (int)slow[1];
-    int v = ce | (cs << 16);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-    if (lane == 31) s_scan[warp] = v;
-    __syncthreads();
-    int base = 0, tot = 0;
-    for (int w = 0; w < 32; w++) { if (w < warp) base += s_scan[w]; tot += s_scan[w]; }
-    const int excl = base + v - (ce | (cs << 16));
-    int de = excl & 0xffff, ds = excl >> 16;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        if (elig[k]) { s_box[de] = box[k]; s_j[de] = 2 * t + k; de++; }
-        if (slow[k]) { wk->slow[ds] = 2 * t + k; ds++; }
-    }
-    if (t == 0) { s_nelig = tot & 0xffff; s_nslow = tot >> 16; }
-    __syncthreads();
-    const int nelig = s_nelig;
-
-    // ---- phase B: warp w owns beam group w (and w+32).  A group gets a window placed on all of its
-    // beams; the beams that do not fit get a second window of their own; what still does not fit is
-    // "wide" and goes to the LDG kernel.
-    const int n_groups = (nelig + kChunkBeams - 1) / kChunkBeams;
-    for (int c = warp; c < n_groups; c += 32) {
-        const int d = c * kChunkBeams + lane;
-        const bool have = d < nelig;
-        const int4 b = have ? s_box[d] : make_int4(0, 0, 0, 0);
-        bool todo = have;
-        double rx = 0, ry = 0, ca = 0, sa = 0;
-        int j = 0;
-        if (have) {
-            j = s_j[d];
-            const double r = (double)scan[j];
+    // ---- this lane's beam
+    const int j = c * kChunkBeams + lane;
+    bool todo = false, slow = false;
+    int4 b = make_int4(0, 0, 0, 0);
+    double rx = 0, ry = 0, ca = 0, sa = 0;
+    if (j < n_beams) {
+        const float r = scan[j];
+        rx = (double)r / (double)g.res_x; ry = (double)r / (double)g.res_y;
+        const bool fast = fabs(rx) < (double)kFastMaxCells && fabs(ry) < (double)kFastMaxCells;   // false for NaN
+        slow = !fast;
+        if (fast) {
+            todo = true;
             const double2 t2 = angle_cs[j];
-            rx = r / (double)g.res_x; ry = r / (double)g.res_y; ca = t2.x; sa = t2.y;
-        }
-        if (lane == 0) { tw->chunk[2 * c].count = 0; tw->chunk[2 * c + 1].count = 0; s_cnt2[2 * c] = 0; s_cnt2[2 * c + 1] = 0; }
-        __syncwarp();
-        for (int pass = 0; pass < 2; pass++) {
-            int x0 = todo ? b.x : 0x3fffffff, x1 = todo ? b.y : -0x3fffffff;
-            int y0 = todo ? b.z : 0x3fffffff, y1 = todo ? b.w : -0x3fffffff;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-                y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-            }
-            const unsigned tm = __ballot_sync(0xffffffffu, todo);
-            if (!tm) break;
-            // fallback anchor when the span is too large: the middle beam still to place
-            const int mid_lane = __fns(tm, 0, (__popc(tm) + 1) / 2);
-            const int mx = (__shfl_sync(0xffffffffu, b.x, mid_lane) + __shfl_sync(0xffffffffu, b.y, mid_lane)) / 2;
-            const int my = (__shfl_sync(0xffffffffu, b.z, mid_lane) + __shfl_sync(0xffffffffu, b.w, mid_lane)) / 2;
-            int ox, oy;
-            if ((long long)x1 - x0 < kTileX - 1) ox = x0 - (kTileX - 1 - (x1 - x0)) / 2;
-            else ox = mx - kTileX / 2;
-            // y is the contiguous dimension of the grid: the TMA box must start on a 16-byte boundary
-            // there (measured on B200: unaligned inner coordinates fault), so the y origin is aligned down
-            if ((long long)y1 - y0 < kTileX - 1) { const int slack = kTileX - 2 - (y1 - y0); oy = y0 - 1 - max(0, slack - 15) / 2; }
-            else oy = my - kTileX / 2;
-            ox = max(-100000, min(100000, ox));
-            oy = (max(-100000, min(100000, oy)) >> 4) << 4;
-            const bool member = todo && b.x >= ox + 1 && b.y <= ox + kTileX - 2 && b.z >= oy + 1 && b.w <= oy + kTileX - 2;
-            const unsigned mm = __ballot_sync(0xffffffffu, member);
-            const int slot = 2 * c + pass;
-            if (member) {
-                const double u = (double)(1 << kFracT);
-                const int k = __popc(mm & ((1u << lane) - 1));
-                tw->tconst[slot * kChunkBeams + k] = make_float4((float)(-rx * sa * u), (float)(ry * ca * u),
-                                                                 (float)(rx * ca * u), (float)(ry * sa * u));
-                tw->tbeam[slot * kChunkBeams + k] = j;
-                todo = false;
-            }
-            if (lane == 0) { TileChunk tc; tc.x0 = ox; tc.y0 = oy; tc.count = __popc(mm); tc.pad = 0; tw->chunk[slot] = tc; s_cnt2[slot] = tc.count; }
-        }
-        const unsigned wm = __ballot_sync(0xffffffffu, todo);
-        if (wm) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_nwide, __popc(wm));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (todo) {
-                const double u = (double)(1 << kFracBits);
-                const int k = wbase + __popc(wm & ((1u << lane) - 1));
-                wk->fconst[k] = make_float4((float)(rx * ca * u), (float)(-rx * sa * u), (float)(ry * ca * u), (float)(ry * sa * u));
-                wk->fbeam[k] = j;
+            ca = t2.x; sa = t2.y;
+            if (cloud_ok) {
+                float cmin, cmax, smin, smax;
+                const float a = angle[j];
+                // interval of rot = angle + theta over the cloud, padded for float rounding
+                trig_range(a + (float)tmin - 4e-6f, a + (float)tmax + 4e-6f, cmin, cmax, smin, smax);
+                const double xa = rx * (double)cmin, xb = rx * (double)cmax, ya = ry * (double)smin, yb = ry * (double)smax;
+                const double vx0 = (double)c0x + pxmin / (double)g.res_x + fmin(xa, xb);
+                const double vx1 = (double)c0x + pxmax / (double)g.res_x + fmax(xa, xb);
+                const double vy0 = (double)c0y + pymin / (double)g.res_y + fmin(ya, yb);
+                const double vy1 = (double)c0y + pymax / (double)g.res_y + fmax(ya, yb);
+                b = make_int4((int)floor(vx0) - kBoxMargin, (int)ceil(vx1) + kBoxMargin,
+                              (int)floor(vy0) - kBoxMargin, (int)ceil(vy1) + kBoxMargin);
+            } else {
+                b = make_int4(-(1 << 20), 1 << 20, -(1 << 20), 1 << 20);   // never fits -> wide
             }
         }
     }
-    __syncthreads();
-    // the score kernel walks the non-empty windows only: compact their slots (beam order kept)
-    if (warp == 0) {
+
+    // ---- up to two windows for the group
+    int cnt2[2] = {0, 0};
+    for (int pass = 0; pass < 2; pass++) {
+        int x0 = todo ? b.x : 0x3fffffff, x1 = todo ? b.y : -0x3fffffff;
+        int y0 = todo ? b.z : 0x3fffffff, y1 = todo ? b.w : -0x3fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        const unsigned tm = __ballot_sync(0xffffffffu, todo);
+        const int slot = 2 * c + pass;
+        if (!tm) { if (lane == 0) { TileChunk tc; tc.x0 = 0; tc.y0 = 0; tc.count = 0; tc.pad = 0; tw->chunk[slot] = tc; } continue; }
+        // fallback anchor when the span is too large: the middle beam still to place
+        const int mid_lane = __fns(tm, 0, (__popc(tm) + 1) / 2);
+        const int mx = (__shfl_sync(0xffffffffu, b.x, mid_lane) + __shfl_sync(0xffffffffu, b.y, mid_lane)) / 2;
+        const int my = (__shfl_sync(0xffffffffu, b.z, mid_lane) + __shfl_sync(0xffffffffu, b.w, mid_lane)) / 2;
+        int ox, oy;
+        if ((long long)x1 - x0 < kTileX - 1) ox = x0 - (kTileX - 1 - (x1 - x0)) / 2;
+        else ox = mx - kTileX / 2;
+        // y is the contiguous dimension of the grid: the TMA box must start on a 16-byte boundary
+        // there (measured on B200: unaligned inner coordinates fault), so the y origin is aligned down
+        if ((long long)y1 - y0 < kTileX - 1) { const int slack = kTileX - 2 - (y1 - y0); oy = y0 - 1 - max(0, slack - 15) / 2; }
+        else oy = my - kTileX / 2;
+        ox = max(-100000, min(100000, ox));
+        oy = (max(-100000, min(100000, oy)) >> 4) << 4;
+        const bool member = todo && b.x >= ox + 1 && b.y <= ox + kTileX - 2 && b.z >= oy + 1 && b.w <= oy + kTileX - 2;
+        const unsigned mm = __ballot_sync(0xffffffffu, member);
+        if (member) {
+            const double u = (double)(1 << kFracT);
+            const int k = __popc(mm & ((1u << lane) - 1));
+            tw->tconst[slot * kChunkBeams + k] = make_float4((float)(-rx * sa * u), (float)(ry * ca * u),
+                                                             (float)(rx * ca * u), (float)(ry * sa * u));
+            tw->tbeam[slot * kChunkBeams + k] = j;
+            todo = false;
+        }
+        cnt2[pass] = __popc(mm);
+        if (lane == 0) { TileChunk tc; tc.x0 = ox; tc.y0 = oy; tc.count = cnt2[pass]; tc.pad = 0; tw->chunk[slot] = tc; }
+    }
+    // ---- what is left goes to k_score_fast: appended to its dense lists (the order across groups does not
+    // matter, scores are integer sums)
+    const unsigned wm = __ballot_sync(0xffffffffu, todo), sm_ = __ballot_sync(0xffffffffu, slow);
+    int wbase = 0, sbase = 0;
+    if (lane == 0) {
+        if (wm) wbase = atomicAdd(&tw->wide_run, __popc(wm));
+        if (sm_) sbase = atomicAdd(&tw->slow_run, __popc(sm_));
+    }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+    if (todo) {
+        const double u = (double)(1 << kFracBits);
+        const int k = wbase + __popc(wm & ((1u << lane) - 1));
+        wk->fconst[k] = make_float4((float)(rx * ca * u), (float)(-rx * sa * u), (float)(ry * ca * u), (float)(ry * sa * u));
+        wk->fbeam[k] = j;
+    }
+    if (slow) wk->slow[sbase + __popc(sm_ & ((1u << lane) - 1))] = j;
+    int last = 0;
+    __threadfence();                           // every lane's entries before the group is counted as done
+    __syncwarp();
+    if (lane == 0) last = atomicAdd(&tw->done, 1) == n_groups - 1;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+
+    // ---- last warp: compact.  Non-empty windows in slot order with their work prefix ...
+    {
         int base_m = 0, run = 0;
         for (int s0 = 0; s0 < 2 * n_groups; s0 += 32) {
             const int sl = s0 + lane;
-            const int cv = sl < 2 * n_groups ? s_cnt2[sl] : 0;
+            const int cv = sl < 2 * n_groups ? __ldcg(&tw->chunk[sl].count) : 0;
             const bool ne = cv > 0;
             const unsigned bm = __ballot_sync(0xffffffffu, ne);
             int inc = ne ? cv + kWindowCostBeams : 0;         // work weight of the window
@@ -282,12 +260,13 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             base_m += __popc(bm);
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 0) {
-            tw->cum[base_m] = run;
-            tw->n_chunks = base_m; wk->nf = s_nwide; wk->ns = s_nslow;
-            // consumed: reset the cloud bounds for the next frame's k_motion
-            for (int c = 0; c < 3; c++) { tw->bounds[2 * c] = 0x7fffffff; tw->bounds[2 * c + 1] = (int)0x80000000; }
-        }
+        if (lane == 0) { tw->cum[base_m] = run; tw->n_chunks = base_m; }
+    }
+    if (lane == 0) {
+        wk->nf = atomicAdd(&tw->wide_run, 0); wk->ns = atomicAdd(&tw->slow_run, 0);
+        // consumed: reset the cloud bounds for the next frame's k_motion, and the per-frame counters
+        for (int q = 0; q < 3; q++) { tw->bounds[2 * q] = 0x7fffffff; tw->bounds[2 * q + 1] = (int)0x80000000; }
+        tw->wide_run = 0; tw->slow_run = 0; tw->done = 0;
     }
 }
 
@@ -728,7 +707,8 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
         k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw, partial);
         nl += 2;
     }
-    k_tile_prep<<<1, 1024, 0, stream>>>(scan, angle, angle_cs, n_beams, g, wk, tw);
+    const int n_prep_groups = (n_beams + kChunkBeams - 1) / kChunkBeams;
+    k_tile_prep<<<(n_prep_groups + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, stream>>>(scan, angle, angle_cs, n_beams, g, wk, tw);
     if (laps) laps->mark(stream, kLapTilePrep);
     if (aux) { cudaEventRecord(ev_fork, stream); cudaStreamWaitEvent(aux, ev_fork, 0); }
     // one full wave; small filters get fewer blocks (an item is the smallest share)
