@@ -4,12 +4,40 @@
 // resample, all on one stream with no host round trip.  Reference semantics per kernel are cited
 // inline (paths relative to michaelwillett/GPU-ICP-SLAM src/).
 #pragma once
+#include <cstdlib>
 #include <vector>
 
 #include "pf_arith.cuh"
 #include "pf_xchg.cuh"
 
 namespace pf {
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the stream-serialization attribute may
+// have its blocks scheduled while the kernel before it is still running, once every block of that kernel
+// has executed pdl_trigger(); it must execute pdl_wait() before touching anything the earlier kernel
+// wrote (the wait returns when that grid has completed and flushed).  Both are no-ops in a normal launch.
+// Used on the step's critical-path edges to hide launch latency (PFSLAM_PDL=0 turns it off).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PFSLAM_PDL"); v = e ? (atoi(e) != 0) : 1; }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(bool dependent, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (dependent && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // host side: per-kernel lap events of the serialised profiling step (pfslam_profile_laps)
 enum { kLapStart = -1, kLapMotion = 0, kLapTilePrep, kLapScoreTiled, kLapScoreFast, kLapCombine, kLapWeights,
@@ -78,6 +106,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
          float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row)
 {
     __shared__ int s_b[6];
+    pdl_trigger();                              // k_tile_prep's blocks may be staged now; they wait for this grid
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,6 +334,8 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
 {
     __shared__ float s_wtot[8], s_wmax[8];
     __shared__ int s_last;
+    pdl_trigger();                              // k_resample's blocks may be staged
+    pdl_wait();                                 // scores and extrema of k_score_combine_rows
     const int seq = sp->seq;
     if (xc.parity_mask) {
         if (threadIdx.x < 32) {
@@ -454,6 +485,7 @@ k_resample(const Xchg xc, const FrameResult *__restrict__ res, const float *__re
            float *__restrict__ th, float *__restrict__ w)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();                                 // k_weights_scan's prefix, decision and tiles
     if (i >= n_local || !res->resampled) return;
     const int frame = sp->frame, seq = sp->seq;
     const float *tiles_all = xc_tiles(xc, seq);

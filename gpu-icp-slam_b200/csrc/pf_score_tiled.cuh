@@ -128,6 +128,8 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             const double2 *__restrict__ angle_cs, int n_beams, MapGeom g,
             ScoreFilteredWork *__restrict__ wk, TiledWork *tw)
 {
+    pdl_trigger();                              // k_score_tiled's blocks may be staged
+    pdl_wait();                                 // k_motion's cloud bounds
     const float *__restrict__ scan = sp->scan;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);       // beam group
@@ -356,6 +358,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
     const int tid = threadIdx.x;
+    pdl_wait();                                 // k_tile_prep's window table
     const int n_chunks = tw->n_chunks;
 
     // the frame's window table and work prefix into shared memory (one parallel round of global loads;
@@ -586,6 +589,7 @@ k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gid
     __shared__ int smin[8];
     __shared__ long long smax[8];
     __shared__ int s_last;
+    pdl_trigger();                              // k_weights_scan's blocks may be staged
     int mn = 0x7fffffff;
     long long mk = (long long)0x8000000000000000ull;
     {
@@ -708,16 +712,17 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
         nl += 2;
     }
     const int n_prep_groups = (n_beams + kChunkBeams - 1) / kChunkBeams;
-    k_tile_prep<<<(n_prep_groups + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, 0, stream>>>(scan, angle, angle_cs, n_beams, g, wk, tw);
+    launch_k(bounds_valid, k_tile_prep, dim3((n_prep_groups + kPrepWarps - 1) / kPrepWarps), dim3(kPrepWarps * 32), 0, stream,
+             scan, angle, angle_cs, n_beams, g, wk, tw);                  // dependent of k_motion when it ran just before
     if (laps) laps->mark(stream, kLapTilePrep);
     if (aux) { cudaEventRecord(ev_fork, stream); cudaStreamWaitEvent(aux, ev_fork, 0); }
     // one full wave; small filters get fewer blocks (an item is the smallest share)
     const int gt = min(tiled_grid, ((n + kTiledGroup - 1) / kTiledGroup) * kMaxChunks);
     if (ev0) cudaEventRecord(ev0, stream);
     if (tiled_threads() == 512)
-        k_score_tiled<512, 2><<<gt, 512, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+        launch_k(true, k_score_tiled<512, 2>, dim3(gt), dim3(512), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     else
-        k_score_tiled<256, 4><<<gt, 256, sizeof(TiledSmem), stream>>>(tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+        launch_k(true, k_score_tiled<256, 4>, dim3(gt), dim3(256), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
     if (laps) laps->mark(stream, kLapScoreTiled);
     dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);          // last row = slow beams

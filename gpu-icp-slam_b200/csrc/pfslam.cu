@@ -71,6 +71,7 @@ struct pfslam_engine {
     TiledWork *twork = nullptr;
     double2 *angle_cs = nullptr;
     bool prefix_fused = false;
+    bool resample_follows_weights = false;   // k_resample is launched right after k_weights_scan on the same stream
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
@@ -684,9 +685,10 @@ static int ph_weights(pfslam_engine *e)
     const bool local_or_peer = e->n_ranks == 1 || e->cur_xc->parity_mask;
     const int fuse = (local_or_peer && e->cfg.path == PFSLAM_PATH_GRID2D && e->n_tiles * e->n_ranks <= kFusedPrefixMaxTiles) ? 1 : 0;
     e->prefix_fused = fuse != 0;
-    k_weights_scan<<<e->n_tiles, kScanThreads, 0, e->stream>>>(*e->cur_xc, e->sp, e->fit, e->w, e->n,
-                                                               e->gidx0, n_sync, e->n_tiles, e->tiles_local, fuse,
-                                                               e->n_global, e->prefix, e->res, 1, e->counters + 5);
+    // dependent launch of the scorer's combine kernel on the grid path (the kd path runs k_extrema before it)
+    launch_k(e->cfg.path == PFSLAM_PATH_GRID2D && e->score_mode == PFSLAM_SCORE_TILED, k_weights_scan, dim3(e->n_tiles), dim3(kScanThreads), 0, e->stream,
+             *e->cur_xc, e->sp, e->fit, e->w, e->n, e->gidx0, n_sync, e->n_tiles, e->tiles_local, fuse,
+             e->n_global, e->prefix, e->res, 1, e->counters + 5);
     if (e->laps_on) e->laps.mark(e->stream, kLapWeights);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -799,8 +801,10 @@ int pfslam_phase_map(pfslam_engine *e, const float *scan_dev)
 static int ph_resample(pfslam_engine *e, int32_t frame)
 {
     { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
-    k_resample<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(*e->cur_xc, e->res, e->prefix, e->n_tiles, e->n, e->n_global,
-                                                           e->gidx0, e->sp, e->x, e->y, e->th, e->w);
+    // dependent launch of k_weights_scan when that kernel is the one just before (prefix fused into it)
+    launch_k(e->resample_follows_weights, k_resample, dim3(ceil_div(e->n, 256)), dim3(256), 0, e->stream,
+             *e->cur_xc, e->res, e->prefix, e->n_tiles, e->n, e->n_global, e->gidx0, e->sp, e->x, e->y, e->th, e->w);
+    e->resample_follows_weights = false;
     if (e->laps_on) e->laps.mark(e->stream, kLapResample);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -985,6 +989,7 @@ static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
     if ((rc = launch_map(e, e->aux, 1))) return rc;
     CUDA_TRY(cudaEventRecord(e->ev_join[1], e->aux));
     if ((rc = ph_weights(e))) return rc;
+    e->resample_follows_weights = e->prefix_fused;
     if ((rc = launch_prefix(e))) return rc;
     if ((rc = ph_resample(e, frame))) return rc;
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[1], 0));
