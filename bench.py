@@ -31,6 +31,13 @@ METRIC = "lidar_frames_per_sec_at_65536_particles_per_gpu"
 UNIT = "frames/s"
 
 
+def synthetic_scans(n_frames):
+    """BASELINE configs[4]: the synthetic 1081-beam corridor workload (gpu-icp-slam_b200/synth.py), frames 1.."""
+    from gpu_icp_slam_b200 import synth
+    sc, _ = synth.generate(n_frames + 1)
+    return np.ascontiguousarray(sc[1:]), list(range(1, n_frames + 1))
+
+
 def workload_scans(n_frames, dataset=None):
     """real train_lidar scans played 1..last..1.. (ping-pong keeps the motion physically continuous
     for any number of steps): the committed 256-frame train_lidar0 fixture, or a full converted
@@ -239,7 +246,10 @@ def run_ours(args):
     n = args.particles
     K, W = args.steps, max(args.warmup, 3)
     kd = args.path == "kd"
-    scans, order = workload_scans(K + W + 8, "train_lidar3" if kd else None)
+    if args.data == "synthetic":
+        scans, order = synthetic_scans(K + W + 8)
+    else:
+        scans, order = workload_scans(K + W + 8, "train_lidar3" if kd else None)
     # everything runs on one non-default stream (the legacy default stream cannot be graph-captured)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -363,7 +373,8 @@ def run_ours(args):
             "metric": METRIC + ("_kd" if kd else ""), "value": K / (dev_ms * 1e-3) * scale, "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
-            "data": "real train_lidar0 scans (committed 256-frame fixture, ping-pong); the full .mat is not on the GPU box",
+            "data": ("synthetic 1081-beam corridor scans @ 40 Hz (gpu-icp-slam_b200/synth.py, PCG64(565))" if args.data == "synthetic" else
+                     "real train_lidar0 scans (committed 256-frame fixture, ping-pong); the full .mat is not on the GPU box"),
             "config": {"workload": ("train_lidar3 (or the train_lidar0 fixture), kd-tree point cloud @ 25 mm, 65 536 particles per GPU" if kd else
                                     "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, 65 536 particles per GPU"),
                        "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS,
@@ -408,6 +419,8 @@ def main():
                     help="multi-GPU: capture the sharded step (kernels + all-gathers) in one CUDA graph (experimental)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
                     help="multi-GPU transport: kernels over NVLink peer memory (default) or NCCL all-gathers between phases")
+    ap.add_argument("--data", default="train_lidar0", choices=["train_lidar0", "synthetic"],
+                    help="scans: the committed train_lidar0 fixture (BASELINE configs[1]) or the synthetic corridor of configs[4]")
     ap.add_argument("--path", default="grid2d", choices=["grid2d", "kd"], help="map representation (BASELINE configs 2 / 3)")
     args = ap.parse_args()
     if args.impl == "reference":
