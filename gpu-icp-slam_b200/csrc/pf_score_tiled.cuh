@@ -1,23 +1,28 @@
-// pf_score_tiled.cuh -- scoring v3: TMA-staged occupancy-grid tiles in shared memory.
+// pf_score_tiled.cuh -- scoring: TMA-staged occupancy-grid windows in shared memory.
 //
 // Same contract as pf_score_filtered.cuh (bit-identical to the reference's kernEvaluateParticles,
 // src/kernel.cu:257-284), restructured for the B200 memory system:
 //
-//   * the dense list of fast beams is cut into chunks of 32 consecutive beams; consecutive beams
-//     hit a contiguous wall segment, so the hit cells of a chunk -- for EVERY particle of the cloud
-//     (conservative interval bound from the cloud's pose bounds) -- fit a 128x128-cell window.
-//     That window is staged into shared memory by one TMA 2D box load per (block, chunk),
-//     double-buffered behind an mbarrier; out-of-map parts are zero-filled by the TMA unit, which
-//     IS the reference's bounds test (out-of-map cells contribute 0, kernel.cu:248);
+//   * the scan is cut into groups of 32 consecutive beams; consecutive beams hit a contiguous wall
+//     segment, so the hit cells of a group -- for EVERY particle of the cloud (conservative interval
+//     bound from the cloud's pose bounds) -- fit a 128x128-cell window (a second window takes the
+//     group's leftovers).  k_tile_prep places the windows, one warp per group;
+//   * a window is staged into shared memory by one TMA 2D box load per (block, window) behind an
+//     mbarrier, the next one in flight while the current one is scored; out-of-map parts are
+//     zero-filled by the TMA unit, which IS the reference's bounds test (kernel.cu:248);
 //   * 2^-16-cell fixed point relative to the window origin inside the float mantissa (magic 2^23):
 //     two packed FFMA2 give both axes; the cell byte of each axis is byte 2 of the result, so ONE
-//     PRMT builds the shared-memory offset (x*256 + y) and one LDS.S8 fetches the cell;
+//     PRMT builds the offset x*256 + y, one LEA.HI skews it to the conflict-avoiding pitch-272 layout
+//     and one LDS.S8 fetches the cell;
 //   * the rounding guard band (+-64 units = +-9.8e-4 cell, error bound 38 units) is
-//     "bits 7..15 == 0"; uncertain pairs set a bit in a per-particle 32-bit mask (one bit per beam of
-//     the chunk), are compacted into a shared-memory queue after the chunk and re-evaluated with
-//     the reference's exact expression;
-//   * beams whose conservative box does not fit the chunk window (depth discontinuities, wide
-//     clouds) go to the v2 LDG kernel (k_score_fast), out-of-domain beams to its exact row.
+//     "bits 7..15 == 0"; uncertain pairs set a bit in a per-particle mask (one bit per beam of the
+//     window), are queued in shared memory and re-evaluated once per particle group with the
+//     reference's exact expression;
+//   * the frame's (particle group, window) items are cut into one equal share per resident block
+//     (grid = SMs x blocks/SM, a single full wave);
+//   * beams whose conservative box does not fit a window (depth discontinuities, wide clouds) go to
+//     the LDG kernel (k_score_fast) on a side branch of the step graph, out-of-domain beams to its
+//     exact row.
 #pragma once
 #include <cuda.h>
 

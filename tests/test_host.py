@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: scan packing, Scene/Lidar mirrors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -45,3 +47,27 @@ def test_scene_parse(tmp_path):
     q.write_text("CAMERA\nRES 1 1\n")
     with pytest.raises(g.PfslamError):
         g.Scene(str(q))
+
+
+def test_map_export_writers(tmp_path):
+    """tools/export_map.py: PGM of an oracle-built grid and PCD of an oracle-built kd cloud are well formed"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("export_map", os.path.join(helpers.ROOT, "tools", "export_map.py"))
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    scans = helpers.fixture_scans()
+    of = helpers.OracleFilter(64)
+    ok = helpers.OracleKdFilter(64)
+    for f in range(1, 6):
+        of.step(scans[f], f)
+        ok.step(scans[f], f)
+    em.write_pgm(str(tmp_path / "m.pgm"), of.grid.reshape(1600, 1600))
+    raw = open(tmp_path / "m.pgm", "rb").read()
+    assert raw.startswith(b"P5\n1600 1600\n255\n") and len(raw) == len(b"P5\n1600 1600\n255\n") + 1600 * 1600
+    px = np.frombuffer(raw[-1600 * 1600:], np.uint8)
+    assert (px == 227).mean() > 0.9 and (px > 227).sum() > 1000 and (px < 227).sum() > 100     # unknown / free / walls
+    em.write_pcd(str(tmp_path / "m.pcd"), ok.tree)
+    lines = open(tmp_path / "m.pcd").read().splitlines()
+    assert lines[1] == "VERSION 0.7" and int(lines[9].split()[1]) == len(ok.tree) == len(lines) - 11
+    of.close()
+    ok.close()
