@@ -81,26 +81,9 @@ __device__ __forceinline__ float *xc_tiles(const Xchg &xc, int seq)
     return xc.tiles_all + (long long)(seq & xc.parity_mask) * xc.n_ranks * xc.tiles_block;
 }
 
-// One thread: wait until every rank's flag of `kind` has reached this step's sequence number.
-// Returns false on timeout (the caller records it in the frame result; nothing hangs).
-__device__ __forceinline__ bool xc_wait(const Xchg &xc, int kind, int seq)
-{
-    if (!xc.parity_mask) return true;
-    const int *f = xc.flags + kind * kMaxRanks;
-    const unsigned long long t0 = xc_now_ns();
-    const unsigned long long limit = (unsigned long long)xc.timeout_ms * 1000000ull;
-    bool ok = true;
-    for (int r = 0; r < xc.n_ranks && ok; r++) {
-        unsigned spins = 0;
-        while (xc_ld_acquire(f + r) - seq < 0) {
-            if ((++spins & 255u) == 0u && xc_now_ns() - t0 > limit) { ok = false; break; }
-        }
-    }
-    return ok;
-}
-
-// The same wait by a whole warp (all 32 lanes call it): lane r polls rank r's flag, so the wait costs
-// one round of latency whatever the rank count.
+// A whole warp (all 32 lanes call it) waits until every rank's flag of `kind` has reached this step's
+// sequence number: lane r polls rank r's flag, so the wait costs one round of latency whatever the rank
+// count.  Returns false on timeout (the caller records it in the frame result; nothing hangs).
 __device__ __forceinline__ bool xc_wait_warp(const Xchg &xc, int kind, int seq)
 {
     if (!xc.parity_mask) return true;
