@@ -98,17 +98,64 @@ __device__ __forceinline__ int kd_nn(const KdNode *__restrict__ tree, float qx, 
 struct KdSearch { float x, y; int lr0, right; };
 constexpr int kKdNoLeft = 0x3fffffff;
 
+// kFormat 1: lr0 = left | axis << 30.
+// kFormat 2 (descent only, for the branch-free visit of kd_nn_flat2): lr0 = left' << 1 | (axis == 1), where
+// left' = right on z-level nodes -- there the reference's test `qz < node.z` is 0 < 0, so the descent
+// always turns right and needs no third case; the parent-plane step reads the 32-byte node instead.
+template <int kFormat>
 __global__ void __launch_bounds__(256)
 k_kd_shadow(const KdNode *__restrict__ tree, const KdState *__restrict__ ks, KdSearch *__restrict__ out, int cap)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap || i >= ks->size) return;
     const KdNode n = kd_load_cg(tree, i);
-    KdSearch s;
-    s.x = n.x; s.y = n.y;
-    s.lr0 = (n.left & kKdNoLeft) | (n.axis << 30);
-    s.right = n.right;
-    reinterpret_cast<int4 *>(out)[i] = make_int4(__float_as_int(s.x), __float_as_int(s.y), s.lr0, s.right);
+    int lr0;
+    if (kFormat == 1) lr0 = (n.left & kKdNoLeft) | (n.axis << 30);
+    else lr0 = ((n.axis == 2 ? n.right : n.left) << 1) | (n.axis == 1 ? 1 : 0);
+    reinterpret_cast<int4 *>(out)[i] = make_int4(__float_as_int(n.x), __float_as_int(n.y), lr0, n.right);
+}
+
+// Same walk over the format-2 shadow with a branch-free visit: the coordinate of the split axis is picked
+// with two selects, the left link is one arithmetic shift.  (kd_nn_flat compiles to ~26 instructions and
+// six branches per visit; ncu shows the scorer issue-bound under divergence)
+__device__ __forceinline__ int kd_nn_flat2(const KdSearch *__restrict__ sh, const KdNode *__restrict__ tree, float qx, float qy)
+{
+    float best2, bestDist;
+    int bestIdx = 0, head = 0;
+    {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(sh));
+        const float dx = __fsub_rn(__int_as_float(v.x), qx), dy = __fsub_rn(__int_as_float(v.y), qy);
+        best2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+        bestDist = __fsqrt_rn(best2);
+    }
+    bool explored = false;
+    for (;;) {
+        while (head >= 0) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(sh) + head);
+            const float nx = __int_as_float(v.x), ny = __int_as_float(v.y);
+            const float dx = __fsub_rn(nx, qx), dy = __fsub_rn(ny, qy);
+            const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            if (d2 < best2) {
+                const float d = __fsqrt_rn(d2);
+                if (d < bestDist) { bestDist = d; best2 = d2; bestIdx = head; explored = false; }
+            }
+            const bool ay = (v.z & 1) != 0;
+            const float qa = ay ? qy : qx, na = ay ? ny : nx;
+            head = qa < na ? (v.z >> 1) : v.w;
+        }
+        if (explored) break;
+        const KdNode b = kd_load(tree, bestIdx);
+        if (b.parent < 0) break;
+        const KdNode p = kd_load(tree, b.parent);
+        bool branch = false; float hd = 0.0f;
+        if (p.axis == 0) { branch = qx < p.x; hd = fabsf(__fsub_rn(qx, p.x)); }
+        if (p.axis == 1) { branch = qy < p.y; hd = fabsf(__fsub_rn(qy, p.y)); }
+        if (p.axis == 2) { branch = 0.0f < p.z; hd = fabsf(__fsub_rn(0.0f, p.z)); }
+        if (!(hd < bestDist)) break;
+        head = !branch ? p.left : p.right;
+        explored = true;
+    }
+    return bestIdx;
 }
 
 __device__ __forceinline__ int kd_nn_flat(const KdSearch *__restrict__ sh, const KdNode *__restrict__ tree, float qx, float qy)
@@ -167,7 +214,7 @@ __global__ void k_kd_nn(const KdNode *__restrict__ tree, const KdState *__restri
 // block = 8 warps, lane = particle, warp w takes beams w, w+8, ...  (Interleaving 4 walks per thread
 // for memory-level parallelism was measured SLOWER, 5.5 vs 3.7 ms: the kernel is bound by divergent
 // instruction issue, not by load latency.)
-template <bool kFlat>
+template <int kFlat>      // 0: generic 32-byte walk, 1: format-1 shadow, 2: format-2 shadow with the branch-free visit
 __global__ void __launch_bounds__(256)
 k_score_kd(const KdNode *__restrict__ tree, const KdSearch *__restrict__ sh, const float *__restrict__ x, const float *__restrict__ y,
            const float *__restrict__ th, int n, int gidx0, const StepParams *__restrict__ sp,
@@ -186,8 +233,9 @@ k_score_kd(const KdNode *__restrict__ tree, const KdSearch *__restrict__ sh, con
             const float r = __ldg(&scan[j]);
             const float wx = __fmul_rn(r, cosf(rot)), wy = __fmul_rn(r, sinf(rot));
             if (fabsf(wx) < kLidarRange && fabsf(wy) < kLidarRange) {
-                const int k = kFlat ? kd_nn_flat(sh, tree, __fadd_rn(wx, px), __fadd_rn(wy, py))
-                                    : kd_nn<false>(tree, __fadd_rn(wx, px), __fadd_rn(wy, py), 0.0f);
+                const int k = kFlat == 2 ? kd_nn_flat2(sh, tree, __fadd_rn(wx, px), __fadd_rn(wy, py))
+                            : kFlat == 1 ? kd_nn_flat(sh, tree, __fadd_rn(wx, px), __fadd_rn(wy, py))
+                                         : kd_nn<false>(tree, __fadd_rn(wx, px), __fadd_rn(wy, py), 0.0f);
                 acc += (int)__ldg(&tree[k].w);
             }
         }

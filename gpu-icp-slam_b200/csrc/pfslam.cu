@@ -85,6 +85,7 @@ struct pfslam_engine {
     KdSearch *kds = nullptr;               // 16-byte search shadow of kd (planar trees)
     int kd_size_ub = 0;                    // host-side upper bound of the device tree size
     bool kd_flat = true;                   // every node has z == 0 and a valid axis: the scorer walks the shadow
+    int kd_walk = 1;                       // shadow format / visit body: 1 (default), 2 = branch-free visit (PFSLAM_KD_WALK=2)
     KdState *ks = nullptr;
     int *bits_blk = nullptr; int n_bits_blk = 0;
     int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 4096;
@@ -292,6 +293,7 @@ static int engine_alloc(pfslam_engine *e)
         e->kd_cap = e->cfg.kd_capacity > 0 ? e->cfg.kd_capacity : (1 << 21);
         CUDA_TRY(cudaMalloc(&e->kd, sizeof(KdNode) * (size_t)e->kd_cap));
         CUDA_TRY(cudaMalloc(&e->kds, sizeof(KdSearch) * (size_t)e->kd_cap));
+        { const char *kw = getenv("PFSLAM_KD_WALK"); e->kd_walk = (kw && atoi(kw) == 2) ? 2 : 1; }
         CUDA_TRY(cudaMalloc(&e->ks, sizeof(KdState)));
         CUDA_TRY(cudaMemsetAsync(e->ks, 0, sizeof(KdState), e->stream));
         e->n_bits_blk = ceil_div((int)(e->bits_bytes / 4), kBitsBlockWords);
@@ -338,7 +340,7 @@ static int preload_kernels()
     PF_PRELOAD(k_beam_prep); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<256, 4>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<512, 2>)); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
     PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
-    PF_PRELOAD(k_score_kd<true>); PF_PRELOAD(k_score_kd<false>); PF_PRELOAD(k_kd_shadow); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
+    PF_PRELOAD(k_score_kd<0>); PF_PRELOAD(k_score_kd<1>); PF_PRELOAD(k_score_kd<2>); PF_PRELOAD(k_kd_shadow<1>); PF_PRELOAD(k_kd_shadow<2>); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
     PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
     PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait);
 #undef PF_PRELOAD
@@ -853,7 +855,8 @@ static int kd_refresh_shadow(pfslam_engine *e, int n_nodes_hint)
     if (n_nodes_hint > 0) e->kd_size_ub = n_nodes_hint;
     const int cover = std::min(e->kd_size_ub, e->kd_cap);
     if (cover <= 0) return PFSLAM_OK;
-    k_kd_shadow<<<ceil_div(cover, 256), 256, 0, e->stream>>>(e->kd, e->ks, e->kds, e->kd_cap);
+    if (e->kd_walk == 2) k_kd_shadow<2><<<ceil_div(cover, 256), 256, 0, e->stream>>>(e->kd, e->ks, e->kds, e->kd_cap);
+    else k_kd_shadow<1><<<ceil_div(cover, 256), 256, 0, e->stream>>>(e->kd, e->ks, e->kds, e->kd_cap);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
@@ -861,12 +864,13 @@ static int kd_refresh_shadow(pfslam_engine *e, int n_nodes_hint)
 
 static void launch_score_kd(pfslam_engine *e)
 {
-    if (e->kd_flat)
-        k_score_kd<true><<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->kds, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
-                                                                   e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
-    else
-        k_score_kd<false><<<ceil_div(e->n, 32), 256, 0, e->stream>>>(e->kd, e->kds, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle,
-                                                                    e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey);
+    const dim3 grid(ceil_div(e->n, 32)), block(256);
+#define PF_SCORE_KD(F) k_score_kd<F><<<grid, block, 0, e->stream>>>(e->kd, e->kds, e->x, e->y, e->th, e->n, e->gidx0, e->sp, e->angle, \
+                                                                    e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey)
+    if (!e->kd_flat) PF_SCORE_KD(0);
+    else if (e->kd_walk == 2) PF_SCORE_KD(2);
+    else PF_SCORE_KD(1);
+#undef PF_SCORE_KD
     e->launches++;
 }
 
