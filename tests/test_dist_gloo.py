@@ -32,6 +32,12 @@ def _worker(rank, world, port, out_dir):
     from fake_engine import OracleShardEngine
     scans = helpers.fixture_scans()
     pf = ShardedParticleFilter(N_TOTAL // world, engine_factory=OracleShardEngine)
+    assert pf.exchange == "collective"            # a stand-in engine cannot use the peer-memory transport
+    try:
+        ShardedParticleFilter(N_TOTAL // world, engine_factory=OracleShardEngine, exchange="peer")
+        raise AssertionError("peer exchange accepted without the CUDA engine")
+    except Exception as ex:
+        assert "CUDA engine" in str(ex), ex
     poses = []
     for f in range(1, FRAMES + 1):
         r = pf.step(scans[f], f)
