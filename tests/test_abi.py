@@ -57,3 +57,27 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle/" not in txt and "liboracle" not in txt and "pfo_" not in txt, os.path.join(dp, f)
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    """no CPU fallback: creating an engine on a box without a CUDA device is an error, not a slow path"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    import gpu_icp_slam_b200 as g
+    with pytest.raises(g.PfslamError, match="cuda"):
+        g.ParticleFilter(128)
+
+
+def test_exchange_api_rejects_bad_arguments_without_gpu():
+    from gpu_icp_slam_b200 import engine
+    lib = engine.load_library()
+    buf = C.create_string_buffer(engine.IPC_HANDLE_BYTES)
+    assert lib.pfslam_ipc_export(None, buf) == 1                      # PFSLAM_ERR_ARG
+    assert lib.pfslam_ipc_connect(None, 0, buf) == 1
+    assert lib.pfslam_connect_peer(None, 0, None) == 1
+    assert lib.pfslam_exchange_ready(None) == 1
+    assert lib.pfslam_lap_name(2) == b"k_score_tiled" and lib.pfslam_lap_name(99) == b""
