@@ -33,7 +33,6 @@ def build(force=False, verbose=False):
 
 
 COMPAT_LIB = os.path.join(HERE, "libpfslam_kernelh.so")
-RUN_BIN = os.path.join(HERE, "pfslam_run")
 
 
 def build_kernel_h_compat(ref="/root/reference"):
@@ -42,9 +41,7 @@ def build_kernel_h_compat(ref="/root/reference"):
     if not os.path.isdir(os.path.join(ref, "src")):
         return None
     src = os.path.join(HERE, "csrc", "kernel_h_compat.cpp")
-    run_src0 = os.path.join(HERE, "csrc", "pfslam_run.cpp")
-    if (os.path.exists(COMPAT_LIB) and os.path.exists(RUN_BIN) and
-            min(os.path.getmtime(COMPAT_LIB), os.path.getmtime(RUN_BIN)) >= max(os.path.getmtime(src), os.path.getmtime(run_src0), os.path.getmtime(LIB))):
+    if os.path.exists(COMPAT_LIB) and os.path.getmtime(COMPAT_LIB) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
         return COMPAT_LIB
     cmd = [os.environ.get("CXX", "g++"), "-std=c++14", "-O2", "-fPIC", "-shared", "-w",
            "-DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP", "-I/usr/local/cuda/include",
@@ -52,17 +49,6 @@ def build_kernel_h_compat(ref="/root/reference"):
            "-o", COMPAT_LIB, src, "-L" + HERE, "-lpfslam", "-Wl,-rpath,$ORIGIN",
            "-L/usr/local/cuda/lib64", "-lcudart"]
     subprocess.run(cmd, check=True)
-    # headless driver with the reference's call sequence (src/main.cpp:175-237) over the same symbols
-    run_src = os.path.join(HERE, "csrc", "pfslam_run.cpp")
-    cmd = [os.environ.get("CXX", "g++"), "-std=c++14", "-O2", "-w",
-           "-DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP", "-I/usr/local/cuda/include",
-           "-I" + os.path.join(ref, "external", "include"), "-I" + os.path.join(ref, "src"),
-           "-o", RUN_BIN, run_src, os.path.join(ROOT, "oracle", "_ref", "scene.o"),
-           os.path.join(ROOT, "oracle", "_ref", "utilities.o"),
-           "-L" + HERE, "-lpfslam_kernelh", "-lpfslam", "-Wl,-rpath,$ORIGIN",
-           "-L/usr/local/cuda/lib64", "-lcudart"]
-    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "scene.o")):
-        subprocess.run(cmd, check=True)
     return COMPAT_LIB
 
 

@@ -55,6 +55,7 @@ struct LapRec {
 constexpr int kTile = 1024;            // reduction / scan tile (pfslam order)
 constexpr int kScanThreads = 256;      // 8 warps x 32 lanes x 4 items
 constexpr int kFusedPrefixMaxTiles = 1024;   // k_weights_scan folds the prefix step in up to 2^20 particles
+constexpr int kMaxPrefixTiles = 4096;        // k_prefix: 2 floats per tile in (default-sized) dynamic shared memory
 constexpr float kLidarRange = 20.0f;   // kernel.cu:44
 constexpr int kFreeWeight = -1;        // kernel.cu:32
 constexpr int kOccupiedWeight = 4;     // kernel.cu:33

@@ -33,6 +33,7 @@ constexpr int kFracBits = 11;
 constexpr int kGuard = 4;                // units of 2^-11 cell
 constexpr float kFastMaxCells = 800.0f;  // |r/res| limit of the fast path
 constexpr float kFastMaxPoseCells = 1000.0f;
+constexpr float kFastMaxTheta = 8.0f;    // |theta| limit of the fast path (ulp of angle + theta, see pslow)
 
 struct ScoreFilteredWork {
     int nf, ns, pad0, pad1;              // fast / slow beam counts of the current frame
@@ -143,7 +144,11 @@ k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict
     sincosf(pth, &sn, &cs);
     const float PX = __fmaf_rn(px, kx, mx), PY = __fmaf_rn(py, ky, mx);
     // particles outside the fast domain (never in practice) are scored exactly, beam by beam
-    const bool pslow = !(fabsf(px) * kx < kFastMaxPoseCells * unit && fabsf(py) * ky < kFastMaxPoseCells * unit);
+    // ... and particles whose heading is large enough for the float rounding of rot = angle + theta (which the
+    // reference has and the fast path has not) to eat the guard band: |theta| < 8 keeps that term below 26 units
+    // of 2^-16 cell at 800 cells of range
+    const bool pslow = !(fabsf(px) * kx < kFastMaxPoseCells * unit && fabsf(py) * ky < kFastMaxPoseCells * unit &&
+                         fabsf(pth) < kFastMaxTheta);
     const int basex = __float_as_int(kMagic) - (ox << kFracBits);
     const int basey = __float_as_int(kMagic) - (oy << kFracBits);
     const unsigned gmask = ((1u << kFracBits) - 1u) & ~(2u * kGuard - 1u);

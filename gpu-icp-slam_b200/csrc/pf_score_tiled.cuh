@@ -42,6 +42,7 @@ constexpr int kTiledQueueCap = 1024;        // (particle, window) records with a
 constexpr float kMagicT = 8388608.0f;       // 2^23
 constexpr int kFracT = 16;
 constexpr float kGuardT = 64.0f;            // units of 2^-16 cell; band test = bits 7..15 zero (error bound 38)
+constexpr double kRotBudgetUnits = 26.0;    // share of the rounding of rot = angle + theta in the 64-unit guard band
 constexpr int kBoxMargin = 2;               // cells added around the conservative hit box
 constexpr int kWindowCostBeams = 8;         // fixed cost of a window (TMA wait, re-layout, two barriers) in beam units
 
@@ -159,7 +160,18 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     if (j < n_beams) {
         const float r = scan[j];
         rx = (double)r / (double)g.res_x; ry = (double)r / (double)g.res_y;
-        const bool fast = fabs(rx) < (double)kFastMaxCells && fabs(ry) < (double)kFastMaxCells;   // false for NaN
+        bool fast = fabs(rx) < (double)kFastMaxCells && fabs(ry) < (double)kFastMaxCells;   // false for NaN
+        // The reference rounds rot = angle + theta to float before its trig (kernel.cu:183); the fast paths do
+        // not, so their distance from the reference grows with ulp(rot) * r.  The error budget
+        // leaves kRotBudgetUnits of 2^-16 cell for that term: beams that exceed it over this cloud's heading
+        // range are scored exactly.  (|rot| < 8 never does; a robot that has turned several times does for
+        // far beams.)
+        if (fast && cloud_ok) {
+            const double a = (double)angle[j];
+            const double rotmax = fmax(fabs(a + tmin), fabs(a + tmax)) + 1e-5;
+            const double half_ulp = ldexp(1.0, max(ilogb(rotmax), 1) - 24);
+            if (half_ulp * fmax(fabs(rx), fabs(ry)) * 65536.0 > kRotBudgetUnits) fast = false;
+        }
         slow = !fast;
         if (fast) {
             todo = true;

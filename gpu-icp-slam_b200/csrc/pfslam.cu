@@ -368,6 +368,14 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
         return set_error(PFSLAM_ERR_UNSUPPORTED, "at most %d ranks", kMaxRanks);
     if (cfg->score_mode < PFSLAM_SCORE_EXACT || cfg->score_mode > PFSLAM_SCORE_TILED)
         return set_error(PFSLAM_ERR_ARG, "bad score_mode");
+    // Every kernel indexes the grid as x * map_w + y, like the reference (kernel.cu:251, :1436), which is only
+    // consistent for square maps; the reference's scene file has one RES and its maps are square.
+    if ((int)(cfg->map_scale_x / cfg->map_res_x) != (int)(cfg->map_scale_y / cfg->map_res_y))
+        return set_error(PFSLAM_ERR_UNSUPPORTED, "non-square maps (%d x %d cells) are not supported",
+                         (int)(cfg->map_scale_x / cfg->map_res_x), (int)(cfg->map_scale_y / cfg->map_res_y));
+    // the global tile prefix (k_prefix / the fused last block) holds 2 floats per 1024-particle tile in shared memory
+    if (((long long)cfg->n_particles_global + kTile - 1) / kTile > kMaxPrefixTiles)
+        return set_error(PFSLAM_ERR_UNSUPPORTED, "at most %d particles in total", kMaxPrefixTiles * kTile);
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev)

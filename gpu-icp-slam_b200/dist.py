@@ -74,7 +74,14 @@ class ShardedParticleFilter:
         if engine_factory is None:
             import torch
             self.engine = _engine.ParticleFilter(self.n, device=device, **kw)
-            self.engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            # The engine's step is one CUDA graph, which cannot be captured on the legacy default stream:
+            # when the caller's current stream is the default one, the engine keeps its own non-default
+            # stream (callers order against it with engine.synchronize() / fetch_result()).
+            # (The collective transport interleaves torch collectives with the engine's phases, so there the
+            # engine must share torch's stream, whatever it is.)
+            cur = torch.cuda.current_stream(device)
+            if cur.cuda_stream != 0 or (self.world > 1 and self.exchange == "collective"):
+                self.engine.set_stream(cur.cuda_stream)
             if self.world == 1:
                 self.exchange = "peer"          # a single shard is just the engine's own graph step
             elif self.exchange == "peer":

@@ -189,7 +189,7 @@ int  pfslam_profile_laps_read(pfslam_engine *e, float ms_mean[PFSLAM_LAP_COUNT],
 const char *pfslam_lap_name(int32_t id);
 
 /* test hook: libdevice cosf/sinf of n host floats evaluated on the device (the functions the
- * reference's kernels call, kernel.cu:185-186); used to validate the oracle's emulation */
+ * reference's kernels call, kernel.cu:185-186); test hook: lets the test suite validate its CPU emulation of them */
 int  pfslam_debug_trig(int32_t device, const float *x_host, int64_t n, float *cos_out, float *sin_out);
 
 #ifdef __cplusplus

@@ -50,13 +50,24 @@ def test_missing_library_fails_loudly(tmp_path):
 
 
 def test_product_does_not_touch_the_oracle():
-    """nothing under gpu-icp-slam_b200/ may import, link or call oracle/"""
-    pkg = os.path.join(helpers.ROOT, "gpu-icp-slam_b200")
-    for dp, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
-                txt = open(os.path.join(dp, f), errors="ignore").read()
-                assert "oracle/" not in txt and "liboracle" not in txt and "pfo_" not in txt, os.path.join(dp, f)
+    """nothing under gpu-icp-slam_b200/ or include/ may import, link, open or call anything of oracle/:
+    the word itself must not occur in any product source (so no path can be assembled from pieces
+    like os.path.join("oracle", ...)), nor the checker's symbol prefix or library names"""
+    banned = ("oracle", "pfo_", "libref", "_ref/", '"_ref"', "'_ref'")
+    for top in ("gpu-icp-slam_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(helpers.ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c", ".txt", ".cmake")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    for b in banned:
+                        assert b not in txt, "%s mentions %r" % (os.path.join(dp, f), b)
+    # and the shipped libraries do not link them
+    import subprocess
+    for so in ("libpfslam.so", "libpfslam_kernelh.so"):
+        p = os.path.join(helpers.ROOT, "gpu-icp-slam_b200", so)
+        if os.path.exists(p):
+            needed = subprocess.run(["readelf", "-d", p], capture_output=True, text=True).stdout
+            assert "oracle" not in needed and "libref" not in needed, so
 
 
 def test_engine_fails_loudly_without_a_gpu():

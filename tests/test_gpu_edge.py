@@ -64,11 +64,11 @@ def test_other_map_geometries(scans, scale, res):
 
 
 def test_headless_driver_over_reference_symbols(tmp_path, scans):
-    """gpu-icp-slam_b200/pfslam_run: the reference's main.cpp call sequence over the reference's own
+    """tools/pfslam_run: the reference's main.cpp call sequence over the reference's own
     symbols (libpfslam_kernelh.so), Scene parsed by the reference's scene.cpp; its trajectory must equal
     the ctypes mirror's bit for bit"""
     import gpu_icp_slam_b200 as g
-    exe = os.path.join(helpers.ROOT, "gpu-icp-slam_b200", "pfslam_run")
+    exe = os.path.join(helpers.ROOT, "tools", "pfslam_run")
     scene = os.path.join(helpers.ORACLE_DIR, "_ref", "map_settings.txt")
     if not (os.path.exists(exe) and os.path.exists(scene)):
         pytest.skip("pfslam_run not built (needs the reference headers at build time)")
