@@ -1131,6 +1131,11 @@ int pfslam_update_grid(pfslam_engine *e, const float *scan_host, const float pos
     CUDA_TRY(cudaMemcpyAsync(e->res, e->h_res, sizeof(FrameResult), cudaMemcpyHostToDevice, e->stream));
     if ((rc = push_params(e, e->scan, e->cur.frame))) return rc;
     e->cur_xc = &e->xc_host;
+    if (e->cfg.path == PFSLAM_PATH_KD) {             // PFUpdateMapKD for an explicit robotPos
+        if ((rc = kd_update_map(e))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        return PFSLAM_OK;
+    }
     if ((rc = clear_map_masks(e, e->stream))) return rc;
     if ((rc = launch_map(e, e->stream, 0))) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -1244,6 +1249,32 @@ int pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_o
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     cudaFree(dq); cudaFree(di);
     if (ce != cudaSuccess) return set_error(PFSLAM_ERR_CUDA, "kd_nn: %s", cudaGetErrorString(ce));
+    return PFSLAM_OK;
+}
+
+int pfslam_kd_icp(pfslam_engine *e, const float *scan_host, const float robot_prev[3], const float start[3], float pose_out[3])
+{
+    if (!e || !scan_host || !robot_prev || !start || !pose_out) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (e->cfg.path != PFSLAM_PATH_KD) return set_error(PFSLAM_ERR_STATE, "engine was not created with PFSLAM_PATH_KD");
+    if (e->kd_empty) return set_error(PFSLAM_ERR_STATE, "no kd tree yet");
+    int rc = pfslam_upload_scan(e, scan_host);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    memset(e->h_res, 0, sizeof(FrameResult));
+    e->h_res->pose[0] = robot_prev[0]; e->h_res->pose[1] = robot_prev[1]; e->h_res->pose[2] = robot_prev[2];
+    CUDA_TRY(cudaMemcpyAsync(e->res, e->h_res, sizeof(FrameResult), cudaMemcpyHostToDevice, e->stream));
+    Extrema ex; memset(&ex, 0, sizeof ex);
+    ex.best_gidx = e->gidx0; ex.x = start[0]; ex.y = start[1]; ex.th = start[2];
+    CUDA_TRY(cudaMemcpyAsync(e->ext_local, &ex, sizeof ex, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = push_params(e, e->scan, e->cur.frame))) return rc;
+    Xchg one = e->xc_host;                           // the start pose is read from a one-rank extrema record
+    one.n_ranks = 1; one.rank = 0; one.ext_all = e->ext_local;
+    k_icp<<<1, 1024, sizeof(float) * 5 * e->cfg.n_beams, e->stream>>>(e->kd, one, e->sp, e->angle, e->cfg.n_beams, e->res);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    pfslam_frame_result r;
+    if ((rc = pfslam_fetch_result(e, &r))) return rc;
+    pose_out[0] = r.pose[0]; pose_out[1] = r.pose[1]; pose_out[2] = r.pose[2];
     return PFSLAM_OK;
 }
 

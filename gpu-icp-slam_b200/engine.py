@@ -102,6 +102,7 @@ _SIGS = {
     "pfslam_kd_nn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pfslam_get_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "pfslam_set_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "pfslam_kd_icp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfslam_launch_count": (C.c_int64, [C.c_void_p]),
     "pfslam_profile_score": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pfslam_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -384,6 +385,14 @@ class ParticleFilter:
         if n.value:
             self._check(self._lib.pfslam_get_kd(self._h, nodes.ctypes.data, n.value, C.byref(n)))
         return nodes[: n.value]
+
+    def kd_icp(self, scan, robot_prev, start):
+        """transformPointICP alone (src/kernel.cu:993): pose = start + one ICP step of `scan` against the
+        tree, targets built from robot_prev (the reference's global robotPos)."""
+        s = _f32(scan, self.n_beams)
+        a, b, out = _f32(robot_prev, 3), _f32(start, 3), np.zeros(3, np.float32)
+        self._check(self._lib.pfslam_kd_icp(self._h, s.ctypes.data, a.ctypes.data, b.ctypes.data, out.ctypes.data))
+        return out
 
     def set_kd(self, nodes):
         a = np.ascontiguousarray(nodes, dtype=np.int32).reshape(-1, 8)

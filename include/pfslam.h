@@ -136,6 +136,13 @@ int  pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_
 /* getPCData's kd part (kernel.cu:810-811): copies up to cap nodes, returns the tree size */
 int  pfslam_get_kd(pfslam_engine *e, void *nodes_out, int32_t cap, int32_t *n_nodes);
 int  pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes);
+/* ICP refinement alone (transformPointICP, kernel.cu:993-1093): one point-to-point step of `scan` against
+ * the tree.  `robot_prev` is the pose the targets are built from (the global robotPos the reference reads
+ * in kernGetWallsKD, kernel.cu:1011), `start` the pose that is corrected (the best particle's). */
+int  pfslam_kd_icp(pfslam_engine *e, const float *scan_host, const float robot_prev[3], const float start[3],
+                   float pose_out[3]);
+/* On a PFSLAM_PATH_KD engine pfslam_update_grid() is PFUpdateMapKD alone (kernel.cu:1406-1540) for an
+ * explicit robotPos: masks, point lists, NN, weight updates, inserts (first call: the first-scan build). */
 
 /* ---- multi-GPU: particles sharded N/R per engine, map replicated (new; the reference is single-GPU) ----
  * Default transport: PEER MEMORY.  Every sharded engine (n_ranks > 1) owns one exchange region;

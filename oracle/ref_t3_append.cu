@@ -44,4 +44,56 @@ void t3_update_map(const float *scan) { std::vector<float> v(scan, scan + LIDAR_
 void t3_resample(int frame) { PFResample(frame); cudaDeviceSynchronize(); }
 int t3_last_error() { return (int)cudaGetLastError(); }
 
+
+/* ---- kd-tree point-cloud path (kernel.cu:816-1540, :1702-1768) ---- */
+void t3_set_alloc_fill(int byte);                  /* oracle/ref_t3_alloc.cu */
+void t3_set_alloc_fill_sized(int byte, size_t size, int byte_special);
+void t3_reset_kd() { kdSize = 0; }                 /* particleFilterInit does not */
+int t3_kd_size() { return kdSize; }
+void t3_kd_set(const void *nodes, int n)
+{
+    memcpy(kd, nodes, (size_t)n * sizeof(KDTree::Node));
+    kdSize = n;
+    cudaMemcpy(dev_kd, kd, (size_t)n * sizeof(KDTree::Node), cudaMemcpyHostToDevice);
+}
+/* the device copy carries the weights (the host copy is refreshed only when a node is inserted) */
+void t3_kd_get(void *nodes) { cudaMemcpy(nodes, dev_kd, (size_t)kdSize * sizeof(KDTree::Node), cudaMemcpyDeviceToHost); }
+void t3_get_fitf(float *fit) { cudaMemcpy(fit, dev_fitf, PARTICLE_COUNT * sizeof(float), cudaMemcpyDeviceToHost); }
+
+/* findCorrespondenceIndexKD (kernel.cu:924) on n query points (x, y, z, w) */
+void t3_kd_nn(const float *q4, int n, int *idx)
+{
+    glm::vec4 *dq = NULL; int *di = NULL;
+    cudaMalloc((void **)&dq, n * sizeof(glm::vec4));
+    cudaMalloc((void **)&di, n * sizeof(int));
+    cudaMemcpy(dq, q4, n * sizeof(glm::vec4), cudaMemcpyHostToDevice);
+    findCorrespondenceIndexKD<<<(n + BLOCK_SIZE - 1) / BLOCK_SIZE, BLOCK_SIZE>>>(n, di, dq, dev_kd);
+    cudaDeviceSynchronize();
+    cudaMemcpy(idx, di, n * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dq); cudaFree(di);
+}
+/* robotPos = PFMeasurementUpdateKD(scan), as particleFilter() does (kernel.cu:1736) */
+void t3_measure_kd(const float *scan, float *pose)
+{
+    std::vector<float> v(scan, scan + LIDAR_SIZE);
+    robotPos = PFMeasurementUpdateKD(v);
+    pose[0] = robotPos.x; pose[1] = robotPos.y; pose[2] = robotPos.z;
+}
+void t3_icp(const float *start, const float *scan, float *out)
+{
+    std::vector<float> v(scan, scan + LIDAR_SIZE);
+    glm::vec3 p = transformPointICP(glm::vec3(start[0], start[1], start[2]), v);
+    out[0] = p.x; out[1] = p.y; out[2] = p.z;
+}
+void t3_update_map_kd(const float *scan) { std::vector<float> v(scan, scan + LIDAR_SIZE); PFUpdateMapKD(v); cudaDeviceSynchronize(); }
+/* the reference's per-frame driver itself (kernel.cu:1702-1768, the kd step at HEAD) */
+void t3_particle_filter(const float *scan, int frame)
+{
+    static Lidar *L = new Lidar(std::string(""));
+    if ((int)L->scans.size() <= frame) L->scans.resize(frame + 1);
+    L->scans[frame].assign(scan, scan + LIDAR_SIZE);
+    particleFilter(NULL, frame, L);
+    cudaDeviceSynchronize();
+}
+
 }

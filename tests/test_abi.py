@@ -43,6 +43,25 @@ def test_default_config_and_arg_errors_without_gpu():
     assert lib.pfslam_destroy(None) == 0                              # Free before Init is harmless
 
 
+def test_unsupported_geometries_are_rejected_without_gpu():
+    """non-square maps (grid indexed x*w+y everywhere, like the reference) and filters beyond the prefix
+    kernel's tile limit are refused at create time, before any CUDA call"""
+    from gpu_icp_slam_b200 import engine
+    lib = engine.load_library()
+    h = C.c_void_p()
+    cfg = engine.Config()
+    lib.pfslam_default_config(C.byref(cfg))
+    cfg.map_scale_x, cfg.map_scale_y = 40.0, 20.0
+    assert lib.pfslam_create(C.byref(cfg), C.byref(h)) == 4          # PFSLAM_ERR_UNSUPPORTED
+    assert b"non-square" in lib.pfslam_last_error()
+    lib.pfslam_default_config(C.byref(cfg))
+    cfg.n_particles = 1024
+    cfg.n_particles_global = 4096 * 1024 + 1024
+    cfg.n_ranks = 4097
+    assert lib.pfslam_create(C.byref(cfg), C.byref(h)) == 4
+    assert b"at most" in lib.pfslam_last_error()
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from gpu_icp_slam_b200 import engine
     with pytest.raises(engine.PfslamError):

@@ -51,6 +51,32 @@ def test_degenerate_scans(scans):
     _run_pair(1500, scans, seq)
 
 
+@pytest.mark.parametrize("theta0", [7.5, 13.0, 25.0, 40.0, -70.0, 2000.0])
+def test_large_headings_stay_exact(scans, theta0):
+    """heading is never wrapped (here or in the reference): after several turns the float rounding of
+    rot = angle + theta grows, and the fast paths must hand the beams / particles it could flip to the exact
+    expression.  Scores of all three scorers == oracle for clouds around |theta| = 7.5 .. 2000 rad."""
+    import ctypes as C
+    import gpu_icp_slam_b200 as g
+    from helpers import P
+    o = helpers.load_oracle()
+    cfg = helpers.ocfg()
+    n = 3000
+    grid = helpers.synth_grid(salt=77)
+    x, y, th = helpers.synth_particles(n, salt=5, spread=0.3, spread_th=0.15, center=(1.0, -2.0, theta0))
+    ones = np.ones(n, np.float32)
+    for f in (3, 120):
+        sc = np.ascontiguousarray(scans[f])
+        want = np.zeros(n, np.int32)
+        o.pfo_score2d_many(C.byref(cfg), P(grid, helpers.bp), P(x), P(y), P(th), n, P(sc), P(want, helpers.ip))
+        for mode in (g.SCORE_EXACT, g.SCORE_FILTERED, g.SCORE_TILED):
+            with g.ParticleFilter(n, score_mode=mode) as pf:
+                pf.set_grid(grid)
+                pf.set_particles(x, y, th, ones)
+                got = pf.score_particles(sc)
+                assert np.array_equal(got, want), "theta0 %g mode %d frame %d: %d scores differ" % (theta0, mode, f, (got != want).sum())
+
+
 def test_other_beam_count(scans):
     """a 720-beam sensor (LIDAR_ANGLE(i) over the first 720 beams)"""
     _run_pair(1000, scans, [(f, scans[f][:720]) for f in range(1, 20)], n_beams=720)

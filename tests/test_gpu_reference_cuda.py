@@ -163,3 +163,237 @@ def test_free_running_against_reference_cuda_path(t3, scans):
         if dmax < 0.08 and na > 200 and nb > 200 and iou > 0.97 and near_ab > 0.9 and near_ba > 0.9:
             return
     raise AssertionError("no attempt agreed with the reference CUDA path: %s" % (seen,))
+
+
+# ---- T3-kd: the kd-tree point-cloud path against the reference's own kd kernels ------------------------------
+# The reference reads device memory it never wrote.  oracle/ref_t3_alloc.cu defines that
+# memory through a link-time wrap of cudaMalloc (the reference's source is untouched): a "stop" record in
+# front of dev_kd (Q9), and a chosen fill byte for fresh blocks -- 0xFF (NaN points, which update nothing)
+# for the tail of dev_free (Q10), 0x00 for the unwritten ICP targets (Q11).  Those are exactly the
+# definitions oracle/pfo_kd.cpp states, so every comparison below is on defined inputs.
+ICP_BUF_BYTES = 1081 * 16
+
+
+@pytest.fixture(scope="module")
+def t3kd(t3):
+    for name in ("t3_kd_set", "t3_kd_get", "t3_kd_nn", "t3_measure_kd", "t3_icp", "t3_update_map_kd", "t3_particle_filter"):
+        if not hasattr(t3, name):
+            pytest.skip("libref_t3.so predates the kd accessors")
+    t3.t3_kd_set.argtypes = [C.c_void_p, C.c_int]
+    t3.t3_kd_get.argtypes = [C.c_void_p]
+    t3.t3_kd_nn.argtypes = [fp, C.c_int, helpers.ip]
+    t3.t3_get_fitf.argtypes = [fp]
+    t3.t3_measure_kd.argtypes = [fp, fp]
+    t3.t3_icp.argtypes = [fp, fp, fp]
+    t3.t3_update_map_kd.argtypes = [fp]
+    t3.t3_particle_filter.argtypes = [fp, C.c_int]
+    t3.t3_set_alloc_fill.argtypes = [C.c_int]
+    t3.t3_set_alloc_fill_sized.argtypes = [C.c_int, C.c_size_t, C.c_int]
+    t3.t3_get_robot.argtypes = [fp]
+    return t3
+
+
+def _grown_tree(scans, n_frames):
+    """(tree int32[n, 8], robot pose) of the oracle's kd filter after n_frames of the fixture"""
+    of = helpers.OracleKdFilter(64)
+    for f in range(1, n_frames + 1):
+        of.step(scans[f], f)
+    tree = of.tree.copy()
+    robot = np.array(list(of.s.contents.robot), np.float32)
+    of.close()
+    return tree, robot
+
+
+def _ref_tree(t3):
+    n = t3.t3_kd_size()
+    out = np.zeros((max(n, 1), 8), np.int32)
+    t3.t3_kd_get(out.ctypes.data)
+    return out[:n]
+
+
+@pytest.mark.parametrize("n_frames", [4, 60, 104, 106])
+def test_kd_nn_equals_reference_kernel(t3kd, scans, n_frames):
+    """findCorrespondenceIndexKD on the B200 == pfslam_kd_nn == the oracle walk, index for index, on trees
+    grown by first-scan build + inserts (4, 60, 104 frames: deep insert chains) and just after the frame-105
+    rebalance; queries near the walls, exactly on nodes, on the root, and far away"""
+    import gpu_icp_slam_b200 as g
+    tree, _ = _grown_tree(scans, n_frames)
+    o = helpers.load_oracle_kd()
+    rng = np.random.default_rng(n_frames)
+    xy = tree[:, 4:6].copy().view(np.float32)
+    q = np.zeros((6000, 4), np.float32)
+    q[:2500, :2] = xy[rng.integers(0, len(tree), 2500)] + rng.normal(0, 0.03, (2500, 2)).astype(np.float32)
+    q[2500:4500, :2] = rng.uniform(-12, 12, (2000, 2)).astype(np.float32)
+    q[4500:5500, :2] = xy[rng.integers(0, len(tree), 1000)]                    # exactly on nodes
+    q[5500:, :2] = xy[0] + rng.normal(0, 0.01, (500, 2)).astype(np.float32)    # around the root (Q9)
+    t3kd.t3_kd_set(tree.ctypes.data, len(tree))
+    ref_idx = np.zeros(len(q), np.int32)
+    t3kd.t3_kd_nn(P(q), len(q), P(ref_idx, helpers.ip))
+    want = np.array([o.pfo_kd_nn(tree.ctypes.data, float(a), float(b), 0.0) for a, b in q[:, :2]], np.int32)
+    assert (want == 0).sum() > 50, "the root-is-best case (Q9) must be exercised"
+    assert np.array_equal(ref_idx, want), "%d of %d NN indices differ from the reference kernel" % ((ref_idx != want).sum(), len(q))
+    with g.ParticleFilter(32, path=g.PATH_KD) as pf:
+        pf.set_kd(tree)
+        got = pf.kd_nn(np.ascontiguousarray(q[:, :3]))
+    assert np.array_equal(got, ref_idx)
+
+
+@pytest.mark.parametrize("n_frames,case", [(30, "tight"), (104, "tight"), (104, "spread")])
+def test_kd_scores_equal_reference_kernel(t3kd, scans, n_frames, case):
+    """kernEvaluateParticlesKD + minmax_element + kernUpdateWeights(float) on the B200: scores identical to
+    the engine's k_score_kd (the reference's float sums are exact integers), same best particle, weights
+    equal to the reference's expression evaluated in IEEE float32"""
+    import gpu_icp_slam_b200 as g
+    tree, robot = _grown_tree(scans, n_frames)
+    kw = dict(tight=dict(spread=0.08, spread_th=0.04), spread=dict(spread=2.0, spread_th=1.0))[case]
+    x, y, th = helpers.synth_particles(N, salt=11, center=tuple(float(v) for v in robot), **kw)
+    ones = np.ones(N, np.float32)
+    t3kd.t3_set_alloc_fill(0)                                  # Q11: unwritten ICP targets are (0,0,0)
+    for f in (n_frames + 1, n_frames + 40):
+        sc = np.ascontiguousarray(scans[f])
+        t3kd.t3_kd_set(tree.ctypes.data, len(tree))
+        t3kd.t3_set_particles(P(x), P(y), P(th), P(ones))
+        t3kd.t3_set_robot(*[C.c_float(float(v)) for v in robot])
+        pose = np.zeros(3, np.float32)
+        t3kd.t3_measure_kd(P(sc), P(pose))
+        fitf = np.zeros(N, np.float32)
+        t3kd.t3_get_fitf(P(fitf))
+        xr, yr, tr, wr = (np.zeros(N, np.float32) for _ in range(4))
+        t3kd.t3_get_particles(P(xr), P(yr), P(tr), P(wr))
+        with g.ParticleFilter(N, path=g.PATH_KD) as pf:
+            pf.set_kd(tree)
+            pf.set_particles(x, y, th, ones)
+            fit = pf.score_particles(sc)
+            assert np.array_equal(fit.astype(np.float32), fitf) and np.array_equal(fit, fitf.astype(np.int64)), \
+                "frame %d: %d kd scores differ from kernEvaluateParticlesKD" % (f, (fit != fitf).sum())
+            best = int(np.argmax(fit))                          # first maximum == thrust::minmax_element
+            mn, mx = int(fit.min()), int(fit.max())
+            if mx > mn:
+                c = np.float32(1.0) / np.float32(mx - mn)
+                w_want = (ones * (fit.astype(np.float32) - np.float32(mn))) * c
+                assert np.array_equal(bits(wr), bits(w_want)), "kernUpdateWeights(float)"
+            # the returned pose is the ICP-corrected best particle: engine == oracle bitwise, reference within
+            # the stated tolerance (thrust::reduce order, svd3.h's approximate Jacobi SVD)
+            mine = pf.kd_icp(sc, robot, [x[best], y[best], th[best]])
+            assert abs(mine[0] - pose[0]) < 2e-4 and abs(mine[1] - pose[1]) < 2e-4 and abs(mine[2] - pose[2]) < 1e-4, \
+                "ICP pose %r vs reference %r" % (mine, pose)
+    t3kd.t3_set_alloc_fill(-1)
+
+
+def test_kd_icp_matches_reference(t3kd, scans):
+    """transformPointICP on the B200 vs pfslam_kd_icp (== the oracle bit for bit): tolerance 2e-4 m / 1e-4 rad,
+    the sum of thrust::reduce's float association over 1081 terms and svd3.h's 4-sweep Jacobi approximation
+    (DESIGN.md 5.3); frames with out-of-range beams included (Q11 defined as zeros on both sides)"""
+    import gpu_icp_slam_b200 as g
+    o = helpers.load_oracle_kd()
+    cfg = helpers.ocfg()
+    t3kd.t3_set_alloc_fill(0)
+    worst = np.zeros(3)
+    for n_frames in (20, 104):
+        tree, robot = _grown_tree(scans, n_frames)
+        t3kd.t3_kd_set(tree.ctypes.data, len(tree))
+        with g.ParticleFilter(32, path=g.PATH_KD) as pf:
+            pf.set_kd(tree)
+            for k, f in enumerate(range(n_frames + 1, n_frames + 25, 3)):
+                sc = np.ascontiguousarray(scans[f])
+                prev = robot + np.float32(0.01 * k) * np.array([1, -1, 0.5], np.float32)
+                start = prev + np.array([0.02, -0.015, 0.01], np.float32)
+                t3kd.t3_set_robot(*[C.c_float(float(v)) for v in prev])
+                ref_out = np.zeros(3, np.float32)
+                t3kd.t3_icp(P(start), P(sc), P(ref_out))
+                mine = pf.kd_icp(sc, prev, start)
+                want = np.zeros(3, np.float32)
+                o.pfo_kd_icp(C.byref(cfg), tree.ctypes.data, P(prev), P(start), P(sc), P(want))
+                assert np.array_equal(bits(mine), bits(want)), "engine ICP != oracle at frame %d" % f
+                worst = np.maximum(worst, np.abs(mine.astype(np.float64) - ref_out))
+    t3kd.t3_set_alloc_fill(-1)
+    assert worst[0] < 2e-4 and worst[1] < 2e-4 and worst[2] < 1e-4, "worst |engine - reference| = %r" % (worst,)
+
+
+def _oracle_update_map(tree, robot, scan, kd_cap=1 << 18):
+    """pfo_kd_update_map on a given tree and robotPos; returns the tree afterwards"""
+    of = helpers.OracleKdFilter(8, kd_cap=kd_cap)
+    s = of.s.contents
+    if len(tree):
+        C.memmove(s.tree, tree.ctypes.data, tree.nbytes)
+    s.kd_size = len(tree)
+    s.robot[0], s.robot[1], s.robot[2] = float(robot[0]), float(robot[1]), float(robot[2])
+    sc = np.ascontiguousarray(scan, np.float32)
+    of.o.pfo_kd_update_map(of.s, P(sc))
+    out = of.tree.copy()
+    of.close()
+    return out
+
+
+def test_kd_first_scan_build_equals_reference(t3kd, scans):
+    """kdSize == 0: PFUpdateMapKD builds the tree with KDTree::Create from the first scan's wall points
+    (kernel.cu:1532-1536); node for node == the engine's first-scan build"""
+    import gpu_icp_slam_b200 as g
+    assert t3kd.t3_init(SCENE.encode()) == 0
+    t3kd.t3_reset_kd()
+    t3kd.t3_set_robot(C.c_float(0), C.c_float(0), C.c_float(0))
+    sc = np.ascontiguousarray(scans[1])
+    t3kd.t3_update_map_kd(P(sc))
+    ref_tree = _ref_tree(t3kd)
+    assert len(ref_tree) > 300
+    with g.ParticleFilter(32, path=g.PATH_KD) as pf:
+        pf.update_grid(sc, [0.0, 0.0, 0.0])
+        assert np.array_equal(pf.get_kd(), ref_tree)
+    assert np.array_equal(_oracle_update_map(np.zeros((0, 8), np.int32), [0, 0, 0], sc), ref_tree)
+
+
+@pytest.mark.parametrize("n_frames", [3, 50, 104])
+def test_kd_map_update_equals_reference(t3kd, scans, n_frames):
+    """PFUpdateMapKD on the B200 (kernGetWalls masks, host point lists, findCorrespondenceIndexKD x2,
+    kernUpdateMapKD x2, kernTestCorrespondance, sequential KDTree::InsertNode) == the engine's device-side map
+    update == the oracle: every node (links, coordinates, weights), over consecutive frames at the robot's
+    pose and at offset poses"""
+    import gpu_icp_slam_b200 as g
+    tree, robot = _grown_tree(scans, n_frames)
+    t3kd.t3_set_alloc_fill(0xFF)                               # Q10: the tail of dev_free is NaN points
+    t3kd.t3_kd_set(tree.ctypes.data, len(tree))
+    cur = tree
+    with g.ParticleFilter(32, path=g.PATH_KD) as pf:
+        pf.set_kd(tree)
+        for k, f in enumerate(range(n_frames + 1, n_frames + 9)):
+            sc = np.ascontiguousarray(scans[f])
+            pose = robot + np.float32(k) * np.array([0.013, -0.008, 0.004], np.float32)
+            t3kd.t3_set_robot(*[C.c_float(float(v)) for v in pose])
+            t3kd.t3_update_map_kd(P(sc))
+            ref_tree = _ref_tree(t3kd)
+            pf.update_grid(sc, pose)
+            mine = pf.get_kd()
+            assert len(mine) == len(ref_tree), "frame %d: %d nodes vs reference %d" % (f, len(mine), len(ref_tree))
+            assert np.array_equal(mine, ref_tree), "frame %d: %d nodes differ" % (f, (mine != ref_tree).any(axis=1).sum())
+            cur = _oracle_update_map(cur, pose, sc)
+            assert np.array_equal(cur, ref_tree), "oracle tree differs at frame %d" % f
+    t3kd.t3_set_alloc_fill(-1)
+
+
+def test_kd_free_running_against_reference_driver(t3kd, scans):
+    """the reference's particleFilter() itself (kernel.cu:1702-1768: the kd step at HEAD, including the
+    frame%100==5 rebalance) against the engine's kd step, both free-running from an empty map at the
+    reference's PARTICLE_COUNT.  Not bit comparable (thrust scan / reduce order, racy in-place resample,
+    approximate SVD); trajectories and trees must agree closely.  Up to three attempts (the reference run
+    is not repeatable)."""
+    import gpu_icp_slam_b200 as g
+    seen = []
+    for _ in range(3):
+        assert t3kd.t3_init(SCENE.encode()) == 0
+        t3kd.t3_reset_kd()
+        t3kd.t3_set_alloc_fill_sized(0xFF, ICP_BUF_BYTES, 0)
+        d, sizes = [], None
+        with g.ParticleFilter(N, path=g.PATH_KD) as pf:
+            for f in range(1, 121):
+                sc = np.ascontiguousarray(scans[f])
+                t3kd.t3_particle_filter(P(sc), f)
+                r = pf.step(sc, f)
+                pose = np.zeros(3, np.float32)
+                t3kd.t3_get_robot(P(pose))
+                d.append(float(np.hypot(r.pose[0] - pose[0], r.pose[1] - pose[1])))
+            sizes = (r.kd_size, t3kd.t3_kd_size())
+        t3kd.t3_set_alloc_fill(-1)
+        seen.append((round(max(d), 4), sizes))
+        if np.isfinite(max(d)) and max(d) < 0.10 and abs(sizes[0] - sizes[1]) < 0.1 * sizes[1]:
+            return
+    raise AssertionError("no attempt agreed with the reference kd driver: %s" % (seen,))
