@@ -35,19 +35,25 @@ def synthetic_scans(n_frames):
     """BASELINE configs[4]: the synthetic 1081-beam corridor workload (gpu-icp-slam_b200/synth.py), frames 1.."""
     from gpu_icp_slam_b200 import synth
     sc, _ = synth.generate(n_frames + 1)
-    return np.ascontiguousarray(sc[1:]), list(range(1, n_frames + 1))
+    return (np.ascontiguousarray(sc[1:]), list(range(1, n_frames + 1)),
+            "synthetic 1081-beam corridor scans @ 40 Hz (gpu-icp-slam_b200/synth.py, PCG64(565))")
 
 
-def workload_scans(n_frames, dataset=None):
+def dataset_path(dataset):
+    """(path, description): the converted full dataset under data/_cache when it travelled to the box, else
+    the committed 256-frame train_lidar0 fixture"""
+    full = os.path.join(ROOT, "data", "_cache", dataset + ".scans.u16")
+    if os.path.exists(full):
+        return full, "real %s scans (data/_cache, first 4000 frames of the .mat, ping-pong)" % dataset
+    return (os.path.join(ROOT, "tests", "golden", "train_lidar0_first256.scans.u16"),
+            "real train_lidar0 scans (committed 256-frame fixture, ping-pong; data/_cache/%s is not on this box)" % dataset)
+
+
+def workload_scans(n_frames, dataset="train_lidar0"):
     """real train_lidar scans played 1..last..1.. (ping-pong keeps the motion physically continuous
-    for any number of steps): the committed 256-frame train_lidar0 fixture, or a full converted
-    dataset from data/_cache when it travelled to the box"""
+    for any number of steps)"""
     from gpu_icp_slam_b200 import scans as S
-    path = os.path.join(ROOT, "tests", "golden", "train_lidar0_first256.scans.u16")
-    if dataset:
-        full = os.path.join(ROOT, "data", "_cache", dataset + ".scans.u16")
-        if os.path.exists(full):
-            path = full
+    path, desc = dataset_path(dataset)
     fx = S.load(path)
     last = min(len(fx) - 1, 4000)
     order, f, d = [], 1, 1
@@ -56,7 +62,25 @@ def workload_scans(n_frames, dataset=None):
         if f + d > last or f + d < 1:
             d = -d
         f += d
-    return np.ascontiguousarray(fx[order]), order
+    return np.ascontiguousarray(fx[order]), order, desc
+
+
+def default_dataset(args):
+    if args.data != "auto":
+        return args.data
+    if args.path == "kd":
+        return "train_lidar3"                      # BASELINE configs[2]
+    return "train_lidar2" if args.gpus == 4 else "train_lidar0"   # configs[3] / configs[1]
+
+
+def make_config(args, world, dataset):
+    """the `config` object; identical in both arms (ours / --impl reference) for the same command line"""
+    n = args.particles
+    kd = args.path == "kd"
+    return {"workload": ("%s, %s, %d particles per GPU x %d" %
+                         (dataset, "kd-tree point cloud @ 25 mm" if kd else "2D occupancy grid 1600x1600 @ 0.025 m", n, world)),
+            "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS, "path": args.path,
+            "value_is": "frames/s x particles_total / 65536 (65 536-particle frame equivalents)"}
 
 
 class ClockSampler:
@@ -131,7 +155,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_frames_per_sec(n_particles, n_frames, threads):
+def cpu_reference_frames_per_sec(n_particles, n_frames, threads, dataset="train_lidar0", warmup=1):
     """The reference's CPU implementation of the path on the host cores: the reference's own
     EvaluateParticle / ParticleAddNoise (oracle/_ref/libref.so, unmodified sources) when that
     library was built, else the oracle port; particle ranges fanned over `threads` host threads
@@ -146,7 +170,7 @@ def cpu_reference_frames_per_sec(n_particles, n_frames, threads):
     # reference-CPU flavour of the arithmetic: libm trig, separate multiply-add (host g++ build)
     cfg = helpers.ocfg(helpers.TRIG_LIBM, helpers.MAD_SEPARATE)
     of = helpers.OracleFilter(n_particles, cfg)
-    scans, order = workload_scans(n_frames + 2)
+    scans, order, _ = workload_scans(n_frames + warmup + 1, dataset)
     bounds = np.linspace(0, n_particles, threads + 1).astype(int)
     fit = np.zeros(n_particles, np.int32)
 
@@ -186,9 +210,10 @@ def cpu_reference_frames_per_sec(n_particles, n_frames, threads):
         o.pfo_update_map(of.s, P(sc))
         o.pfo_resample(of.s, f)
 
-    frame(0)                                  # warm the map
+    for i in range(warmup):                   # warm the map
+        frame(i)
     t0 = time.perf_counter()
-    for i in range(1, n_frames + 1):
+    for i in range(warmup, warmup + n_frames):
         frame(i)
     dt = time.perf_counter() - t0
     of.close()
@@ -203,27 +228,83 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+    dataset = default_dataset(args)
     # same workload as our arm at --gpus N: the whole filter (N x particles-per-GPU) on the host cores,
     # reported in the same unit (65 536-particle frame equivalents per second)
-    n = args.particles * max(1, args.gpus)
-    # each "step" = one frame; bound the whole run to a couple of minutes
+    n = args.particles * world
+    W = max(args.warmup, 3)
+    # each "step" = one frame; bound the whole run (warm-up included) to a few minutes
     per_frame_guess = n * N_BEAMS * 35e-9 / max(1, threads * 0.8) + n * 1.2e-6
-    budget = 150.0
-    k = max(1, min(args.steps, int(budget / max(per_frame_guess, 1e-3))))
-    fps, kind, what = cpu_reference_frames_per_sec(n, k, threads)
+    budget = 240.0
+    k = max(1, min(args.steps, int(budget / max(per_frame_guess, 1e-3)) - W))
+    fps, kind, what = cpu_reference_frames_per_sec(n, k, threads, dataset, W)
     fps_raw = fps
     fps = fps * n / 65536.0
+    _, _, desc = workload_scans(1, dataset)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": k, "warmup": 1, "ms_per_step": 1e3 / fps_raw, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "real train_lidar0 scans (committed 256-frame fixture, ping-pong)",
-        "config": {"workload": "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, %d particles, CPU" % n,
-                   "particles_per_gpu": args.particles, "particles_total": n, "beams": N_BEAMS,
-                   "value_is": "frames/s x particles_total / 65536 (65 536-particle frame equivalents, as in our arm)"},
+        "impl": "reference", "metric": METRIC + ("_kd" if args.path == "kd" else ""), "value": fps, "unit": UNIT, "n_gpus": world,
+        "steps": k, "warmup": W, "ms_per_step": 1e3 / fps_raw, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": desc,
+        "config": make_config(args, world, dataset),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": kind, "sample": what},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.path == "kd":
+        line["note"] = ("the reference has no CPU kd search (SURVEY 8d): this arm times the reference's CPU 2D scoring path "
+                        "on the same scans and particle count")
     print(json.dumps(line), flush=True)
+
+
+def reference_gpu_leg(scans, order, n_warm, n_timed, kd):
+    """The "beat this kernel" bar: the reference's own kernel.cu, compiled for sm_100 with
+    PARTICLE_COUNT patched to 65536 at build time (oracle/_ref/libref_t3_65536.so), on this GPU, on the same
+    scans: wall clock per step the reference's own way (its calls block), and kernEvaluateParticles[KD] alone
+    by CUDA events."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_t3_65536.so")
+    scene = os.path.join(ROOT, "oracle", "_ref", "map_settings.txt")
+    if not (os.path.exists(so) and os.path.exists(scene)):
+        return {"unavailable": "oracle/_ref/libref_t3_65536.so not built (needs /root/reference at build time)"}
+    fp = C.POINTER(C.c_float)
+    lib = C.CDLL(so)
+    lib.t3_init.argtypes = [C.c_char_p]
+    lib.t3_step2d_ms.restype = C.c_double
+    lib.t3_step2d_ms.argtypes = [fp, C.c_int, C.POINTER(C.c_double)]
+    lib.t3_step_kd_ms.restype = C.c_double
+    lib.t3_step_kd_ms.argtypes = [fp, C.c_int]
+    lib.t3_time_evaluate_ms.restype = C.c_float
+    lib.t3_time_evaluate_ms.argtypes = [fp, C.c_int, C.c_int]
+    lib.t3_set_alloc_fill_sized.argtypes = [C.c_int, C.c_size_t, C.c_int]
+    if lib.t3_init(scene.encode()) != 0:
+        return {"unavailable": "t3_init failed"}
+    lib.t3_reset_kd()
+    if kd:
+        lib.t3_set_alloc_fill_sized(0xFF, N_BEAMS * 16, 0)      # defined memory for SURVEY Q10 / Q11
+    n_part = lib.t3_particle_count()
+    phases = np.zeros(4)
+    tot, resampled_ms = [], []
+    ph = (C.c_double * 4)()
+    for i in range(n_warm + n_timed):
+        sc = np.ascontiguousarray(scans[i], np.float32)
+        ms = lib.t3_step_kd_ms(sc.ctypes.data_as(fp), order[i]) if kd else lib.t3_step2d_ms(sc.ctypes.data_as(fp), order[i], ph)
+        if i >= n_warm:
+            tot.append(ms)
+            if not kd:
+                phases += np.array(list(ph))
+    sc = np.ascontiguousarray(scans[n_warm + n_timed - 1], np.float32)
+    score_ms = float(lib.t3_time_evaluate_ms(sc.ctypes.data_as(fp), 5, 1 if kd else 0))
+    out = {"kind": "reference kernel.cu, PARTICLE_COUNT patched to %d at build time, -arch=sm_100, same GPU, same scans" % n_part,
+           "particles": n_part, "steps": n_timed, "warmup": n_warm,
+           "ms_per_step": float(np.mean(tot)), "ms_per_step_median": float(np.median(tot)),
+           "frames_per_sec": 1e3 / float(np.mean(tot)),
+           "scoring_kernel": "kernEvaluateParticlesKD" if kd else "kernEvaluateParticles", "scoring_ms": score_ms,
+           "timing": "wall clock around the reference's blocking step functions (its own method, kernel.cu:1727-1748); scoring kernel by CUDA events"}
+    if not kd:
+        out["phases_ms"] = dict(zip(["motion", "measurement", "map", "resample"], [float(v) / n_timed for v in phases]))
+    else:
+        out["kd_size"] = int(lib.t3_kd_size())
+    lib.t3_init(scene.encode())            # frees the 320 MB device tree of this run; fresh state
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -246,10 +327,14 @@ def run_ours(args):
     n = args.particles
     K, W = args.steps, max(args.warmup, 3)
     kd = args.path == "kd"
-    if args.data == "synthetic":
-        scans, order = synthetic_scans(K + W + 8)
+    dataset = default_dataset(args)
+    # kd path: the tree has to grow to a realistic size before anything is timed (the reference reports
+    # 200-500 k points for whole runs): --prewarm frames of the trajectory, untimed
+    PW = args.prewarm if args.prewarm >= 0 else (2000 if kd else 0)
+    if dataset == "synthetic":
+        scans, order, data_desc = synthetic_scans(PW + K + W + 8)
     else:
-        scans, order = workload_scans(K + W + 8, "train_lidar3" if kd else None)
+        scans, order, data_desc = workload_scans(PW + K + W + 8, dataset)
     # everything runs on one non-default stream (the legacy default stream cannot be graph-captured)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -278,12 +363,15 @@ def run_ours(args):
             pf.step_async(order[i], scans_dev[i].data_ptr())
 
     # ---- warm-up (untimed): builds the map, first-launch costs
-    for i in range(W):
+    for i in range(PW + W):
         step_async(i)
         if world > 1 and i == 2 and args.graph:
             sync_all()
             pf.enable_graph()
     sync_all()
+    scans, order, scans_dev = scans[PW:], order[PW:], scans_dev[PW:]
+    eng0 = pf.engine if world > 1 else pf
+    resample_count0 = eng0.fetch_result().resample_count
 
     # ---- `value`: K steps, inputs resident in HBM, device time per step by CUDA events on the launch
     # stream, L2 flushed (256 MiB memset, untimed) between steps
@@ -303,6 +391,7 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = pf.launch_count - l0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    resampled_steps = eng0.fetch_result().resample_count - resample_count0
 
     # back-to-back (no flush) for reference: the streaming steady state
     sync_all()
@@ -374,17 +463,16 @@ def run_ours(args):
             "metric": METRIC + ("_kd" if kd else ""), "value": K / (dev_ms * 1e-3) * scale, "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
-            "data": ("synthetic 1081-beam corridor scans @ 40 Hz (gpu-icp-slam_b200/synth.py, PCG64(565))" if args.data == "synthetic" else
-                     "real train_lidar0 scans (committed 256-frame fixture, ping-pong); the full .mat is not on the GPU box"),
-            "config": {"workload": ("train_lidar3 (or the train_lidar0 fixture), kd-tree point cloud @ 25 mm, 65 536 particles per GPU" if kd else
-                                    "train_lidar0, 2D occupancy grid 1600x1600 @ 0.025 m, 65 536 particles per GPU"),
-                       "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS,
+            "data": data_desc,
+            "config": dict(make_config(args, world, dataset), **{
                        "score_mode": "tiled (TMA-staged smem windows, bit-exact)", "l2_flush": "256 MiB memset between timed steps (untimed)",
                        "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
                        "parallelism": "particles sharded %d-way, map replicated" % world,
+                       "prewarm_frames": PW,
                        "exchange": ("none (single GPU)" if world == 1 else
                                     "in-kernel stores/loads over NVLink peer memory, whole step = 1 CUDA graph per rank" if args.exchange == "peer"
-                                    else "3 NCCL all-gathers between the step's phases")},
+                                    else "3 NCCL all-gathers between the step's phases")}),
+            "resampled_steps": int(resampled_steps),
             "value_back_to_back": K / (b2b_ms * 1e-3) * scale,
             "wall_s_timed_region": t_wall,
             "e2e": {"value": K / (e2e_ms * 1e-3) * scale, "unit": UNIT,
@@ -400,9 +488,27 @@ def run_ours(args):
             "last_frame": {"neff": r.neff, "resampled": r.resampled, "n_slow_evals": r.n_slow_evals,
                            "slow_eval_frac": r.n_slow_evals / float(n * N_BEAMS), "kd_size": r.kd_size},
         }
-        if not args.no_cpu and world == 1 and not kd:
-            fps, kind, what = cpu_reference_frames_per_sec(n, max(2, min(8, int(20.0 / (n * N_BEAMS * 35e-9 + 1e-3)))), 1)
+        if not args.no_cpu and world == 1:
+            fps, kind, what = cpu_reference_frames_per_sec(n, max(2, min(8, int(20.0 / (n * N_BEAMS * 35e-9 + 1e-3)))), 1,
+                                                           "train_lidar0" if dataset == "synthetic" else dataset)
+            if kd:
+                what += " (the reference has no CPU kd search: its CPU 2D scoring path on the same scans)"
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": kind, "sample": what}
+        if not args.no_refgpu and world == 1 and n == 65536:
+            pf.close()
+            del flush
+            torch.cuda.empty_cache()
+            nt = min(K, 100 if not kd else 60)
+            # kd: the reference's step costs tens of ms at this particle count, so its tree is grown over fewer
+            # frames than ours (a smaller tree favours the reference)
+            rpw = min(PW, args.refgpu_prewarm) if kd else 0
+            wsc, word, _ = (synthetic_scans if dataset == "synthetic" else (lambda m: workload_scans(m, dataset)))(rpw + W + nt)
+            rg = reference_gpu_leg(wsc, word, rpw + W, nt, kd)
+            rg["prewarm_frames"] = rpw
+            line["reference_gpu"] = rg
+            if "ms_per_step" in rg:
+                rg["ours_over_reference_step"] = rg["ms_per_step"] / (dev_ms / K)
+                rg["ours_over_reference_scoring_kernel"] = rg["scoring_ms"] / ker
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -420,8 +526,12 @@ def main():
                     help="multi-GPU: capture the sharded step (kernels + all-gathers) in one CUDA graph (experimental)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
                     help="multi-GPU transport: kernels over NVLink peer memory (default) or NCCL all-gathers between phases")
-    ap.add_argument("--data", default="train_lidar0", choices=["train_lidar0", "synthetic"],
-                    help="scans: the committed train_lidar0 fixture (BASELINE configs[1]) or the synthetic corridor of configs[4]")
+    ap.add_argument("--data", default="auto", choices=["auto", "train_lidar0", "train_lidar2", "train_lidar3", "synthetic"],
+                    help="scans: auto = the dataset BASELINE.json names for this path / GPU count (configs[1..3]); "
+                         "synthetic = the corridor of configs[4]")
+    ap.add_argument("--prewarm", type=int, default=-1, help="untimed frames before the warm-up (default: 2000 on the kd path, else 0)")
+    ap.add_argument("--refgpu-prewarm", type=int, default=300, help="kd path: frames the reference-GPU leg grows its tree over")
+    ap.add_argument("--no-refgpu", action="store_true", help="skip the reference-kernel-on-this-GPU leg")
     ap.add_argument("--path", default="grid2d", choices=["grid2d", "kd"], help="map representation (BASELINE configs 2 / 3)")
     args = ap.parse_args()
     if args.impl == "reference":

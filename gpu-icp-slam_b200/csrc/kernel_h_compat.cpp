@@ -9,10 +9,12 @@
 //
 // Differences from the reference, all at the boundary: the particle count is the run-time value
 // PFSLAM_PARTICLE_COUNT (environment, default 1000 = kernel.cu:30) instead of a #define; the 2D
-// occupancy-grid step runs (the reference's HEAD calls the kd variants) unless
-// PFSLAM_PATH=kd; drawMap is a no-op (rendering is out of scope).
+// occupancy-grid step runs unless PFSLAM_PATH=kd selects the kd-tree point-cloud step -- the one the
+// reference's HEAD calls (kernel.cu:1714-1745); drawMap is a no-op (rendering is out of scope,
+// SURVEY section 2).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "kernel.h"
@@ -24,6 +26,8 @@ static std::vector<Particle> particles;          // getPCData lends these, like 
 static std::vector<MAP_TYPE> occupancyGrid;
 static glm::vec3 robotPos(0.0f);
 static int particle_count = 1000;
+static bool kd_path = false;
+static std::vector<unsigned char> kd;            // getPCData lends these too (kernel.cu:78, :810): raw KDTree::Node records
 
 static void die(const char *what)
 {
@@ -46,6 +50,13 @@ void particleFilterInit(Scene *scene)
     const Patch &m = scene->maps[0];                 // kernel.cu:119
     cfg.map_scale_x = m.scale.x; cfg.map_scale_y = m.scale.y;
     cfg.map_res_x = m.resolution.x; cfg.map_res_y = m.resolution.y;
+    const char *path = getenv("PFSLAM_PATH");
+    kd_path = path && strcmp(path, "kd") == 0;
+    if (path && !kd_path && strcmp(path, "grid2d") != 0) {
+        fprintf(stderr, "pfslam error: PFSLAM_PATH must be grid2d or kd, not '%s'\n", path);
+        exit(EXIT_FAILURE);
+    }
+    cfg.path = kd_path ? PFSLAM_PATH_KD : PFSLAM_PATH_GRID2D;
     const char *dev = getenv("PFSLAM_DEVICE");
     if (dev) cfg.device = atoi(dev);
     if (pfslam_create(&cfg, &g_engine) != PFSLAM_OK) die("particleFilterInit");
@@ -91,5 +102,14 @@ void getPCData(Particle **ptrParticles, MAP_TYPE **ptrMap, KDTree::Node **ptrKD,
     *nParticles = particle_count;
     *ptrKD = NULL;                                   // 2D path: no kd nodes
     *nKD = 0;
+    if (kd_path) {                                   // kernel.cu:810-811: the host copy of the tree and its size
+        int32_t n = 0;
+        static_assert(sizeof(KDTree::Node) == 32, "KDTree::Node layout");
+        if (pfslam_get_kd(g_engine, NULL, 0, &n) != PFSLAM_OK) die("getPCData");
+        if ((size_t)n * sizeof(KDTree::Node) > kd.size()) kd.resize(((size_t)n + 4096) * sizeof(KDTree::Node));
+        if (n > 0 && pfslam_get_kd(g_engine, kd.data(), n, &n) != PFSLAM_OK) die("getPCData");
+        *ptrKD = reinterpret_cast<KDTree::Node *>(kd.data());
+        *nKD = n;
+    }
     pos = robotPos;
 }

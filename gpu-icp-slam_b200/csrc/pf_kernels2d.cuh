@@ -75,6 +75,7 @@ struct FrameResult {
     int   resampled, n_free, n_wall, n_slow;
     int   kd_size, kd_ins;
     int   xchg_timeout;        // sharded engines: a peer-exchange wait ran into its time limit this frame
+    int   resample_count;      // steps that resampled so far
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
@@ -480,7 +481,7 @@ k_prefix(const Xchg xc, const StepParams *__restrict__ sp, int n_tiles_local, in
 // the two-level binary search returns the reference's linear-scan index.  Sharded over peer memory
 // the drawn particle's pose is loaded from its owner's snapshot (xc.pose_src[owner], NVLink).
 __global__ void __launch_bounds__(256)
-k_resample(const Xchg xc, const FrameResult *__restrict__ res, const float *__restrict__ prefix,
+k_resample(const Xchg xc, FrameResult *res, const float *__restrict__ prefix,
            int n_tiles_local, int n_local, int n_global, int gidx0,
            const StepParams *__restrict__ sp, float *__restrict__ x, float *__restrict__ y,
            float *__restrict__ th, float *__restrict__ w)
@@ -488,6 +489,7 @@ k_resample(const Xchg xc, const FrameResult *__restrict__ res, const float *__re
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();                                 // k_weights_scan's prefix, decision and tiles
     if (i >= n_local || !res->resampled) return;
+    if (i == 0) res->resample_count++;
     const int frame = sp->frame, seq = sp->seq;
     const float *tiles_all = xc_tiles(xc, seq);
     const int nt = (n_global + kTile - 1) / kTile;   // == n_ranks * n_tiles_local when sharded

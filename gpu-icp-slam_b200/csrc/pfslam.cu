@@ -1086,6 +1086,7 @@ static void copy_result(const FrameResult *r, pfslam_frame_result *out)
     out->n_slow_evals = r->n_slow;
     out->kd_size = r->kd_size; out->kd_inserted = r->kd_ins;
     out->exchange_timeout = r->xchg_timeout;
+    out->resample_count = r->resample_count;
 }
 
 int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)

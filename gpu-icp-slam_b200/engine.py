@@ -51,7 +51,7 @@ class FrameResult(C.Structure):
         ("best_index", C.c_int32), ("sum_w", C.c_float), ("sum_w2", C.c_float), ("neff", C.c_float),
         ("resampled", C.c_int32), ("n_free_cells", C.c_int32), ("n_wall_cells", C.c_int32),
         ("n_slow_evals", C.c_int32), ("kd_size", C.c_int32), ("kd_inserted", C.c_int32),
-        ("exchange_timeout", C.c_int32),
+        ("exchange_timeout", C.c_int32), ("resample_count", C.c_int32),
     ]
 
     def as_dict(self):

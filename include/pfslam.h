@@ -75,6 +75,7 @@ typedef struct pfslam_frame_result {
     int32_t kd_size;             /* kd path: nodes in the tree after this frame (kdSize, kernel.cu:80) */
     int32_t kd_inserted;         /* kd path: nodes inserted this frame */
     int32_t exchange_timeout;    /* sharded engines: 1 once a peer-exchange wait hit its time limit (results invalid) */
+    int32_t resample_count;      /* steps that resampled so far (reset by the explicit-pose test entry points) */
 } pfslam_frame_result;
 
 /* ---- life cycle: particleFilterInit(Scene*) / particleFilterFree(), kernel.cu:107-178 ---- */

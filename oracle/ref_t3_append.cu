@@ -96,4 +96,64 @@ void t3_particle_filter(const float *scan, int frame)
     cudaDeviceSynchronize();
 }
 
+
+/* ---- timing accessors for bench.py's reference_gpu leg (the "beat this kernel" bar) ---- */
+static double t3_now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+/* one 2D occupancy-grid step in the README.md:41-50 order, timed the reference's own way (wall clock
+ * around blocking calls, kernel.cu:1727-1748); phase_ms[4] = motion, measurement, map, resample */
+double t3_step2d_ms(const float *scan, int frame, double *phase_ms)
+{
+    std::vector<float> v(scan, scan + LIDAR_SIZE);
+    cudaDeviceSynchronize();
+    const double t0 = t3_now_ms();
+    PFMotionUpdate(frame);
+    const double t1 = t3_now_ms();
+    robotPos = PFMeasurementUpdate(v);
+    const double t2 = t3_now_ms();
+    PFUpdateMap(v);
+    cudaDeviceSynchronize();
+    const double t3 = t3_now_ms();
+    PFResample(frame);
+    cudaDeviceSynchronize();
+    const double t4 = t3_now_ms();
+    if (phase_ms) { phase_ms[0] = t1 - t0; phase_ms[1] = t2 - t1; phase_ms[2] = t3 - t2; phase_ms[3] = t4 - t3; }
+    return t4 - t0;
+}
+/* the kd step at HEAD through the reference's own driver, wall clock */
+double t3_step_kd_ms(const float *scan, int frame)
+{
+    cudaDeviceSynchronize();
+    const double t0 = t3_now_ms();
+    t3_particle_filter(scan, frame);
+    return t3_now_ms() - t0;
+}
+/* kernEvaluateParticles (kd != 0: kernEvaluateParticlesKD) alone, CUDA events, mean of reps launches */
+float t3_time_evaluate_ms(const float *scan, int reps, int kd_path)
+{
+    const int blockSize1d = 128;
+    const dim3 blocksPerGrid1d((PARTICLE_COUNT + blockSize1d - 1) / blockSize1d);
+    cudaMemcpy(dev_lidar, scan, LIDAR_SIZE * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(dev_particles, particles, PARTICLE_COUNT * sizeof(Particle), cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float tot = 0.0f;
+    for (int r = 0; r <= reps; r++) {             /* launch 0 is a warm-up */
+        cudaEventRecord(e0);
+        if (kd_path)
+            kernEvaluateParticlesKD<<<blocksPerGrid1d, blockSize1d>>>(dev_occupancyGrid, map_dim, map_params, dev_particles, robotPos, dev_lidar, dev_fitf, dev_kd, kdSize);
+        else
+            kernEvaluateParticles<<<blocksPerGrid1d, blockSize1d>>>(dev_occupancyGrid, map_dim, map_params, dev_particles, robotPos, dev_lidar, dev_fit);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r) tot += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return tot / (float)reps;
+}
+
 }

@@ -95,6 +95,7 @@ def load_oracle():
     for f in ("pfo_measure", "pfo_update_map"):
         getattr(o, f).argtypes = [C.POINTER(OState), fp]
     o.pfo_step2d.argtypes = [C.POINTER(OState), fp, C.c_int]
+    o.pfo_measure_scored.argtypes = [C.POINTER(OState)]
     _oracle = o
     return o
 
@@ -195,6 +196,32 @@ class OracleFilter:
         sc = np.ascontiguousarray(scan, dtype=np.float32)
         self.o.pfo_step2d(self.s, P(sc), int(frame))
         return self.s.contents
+
+    def step_threaded(self, scan, frame, threads=None):
+        """pfo_step2d with the scoring loop fanned over host threads by particle range (ctypes releases the
+        GIL); the same functions in the same order, so the result is identical to step()"""
+        import threading
+        threads = threads or min(32, os.cpu_count() or 1)
+        sc = np.ascontiguousarray(scan, dtype=np.float32)
+        o, s = self.o, self.s
+        o.pfo_motion(s, int(frame))
+        b = np.linspace(0, self.n, threads + 1).astype(int)
+        x, y, th, fit = self.x, self.y, self.th, self.fit
+
+        def work(k):
+            a, e = int(b[k]), int(b[k + 1])
+            if e > a:
+                o.pfo_score2d_many(C.byref(self.cfg), s.contents.grid, P(x[a:e]), P(y[a:e]), P(th[a:e]), e - a, P(sc),
+                                   P(fit[a:e], ip))
+        ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        o.pfo_measure_scored(s)
+        o.pfo_update_map(s, P(sc))
+        o.pfo_resample(s, int(frame))
+        return s.contents
 
 
 # ---- kd path ---------------------------------------------------------------------------------------

@@ -109,3 +109,27 @@ def test_headless_driver_over_reference_symbols(tmp_path, scans):
         for f in range(1, 41):
             p = pf.step(scans[f], f).pose
             assert np.array_equal(bits(traj[f - 1, 1:4]), bits(list(p))), "frame %d" % f
+
+
+def test_headless_driver_kd_path_over_reference_symbols(tmp_path, scans):
+    """the same driver with PFSLAM_PATH=kd: particleFilter() runs the kd step (what the reference's HEAD runs,
+    kernel.cu:1714-1745) and getPCData lends the tree (kernel.cu:810-811); trajectory, node count and weight
+    sum equal the ctypes mirror's"""
+    import gpu_icp_slam_b200 as g
+    exe = os.path.join(helpers.ROOT, "tools", "pfslam_run")
+    scene = os.path.join(helpers.ORACLE_DIR, "_ref", "map_settings.txt")
+    if not (os.path.exists(exe) and os.path.exists(scene)):
+        pytest.skip("pfslam_run not built (needs the reference headers at build time)")
+    csv = tmp_path / "traj_kd.csv"
+    env = dict(os.environ, PFSLAM_PARTICLE_COUNT="1024", PFSLAM_PATH="kd")
+    r = subprocess.run([exe, scene, os.path.join(helpers.GOLDEN, "train_lidar0_first256.scans.u16"), "30", str(csv)],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    traj = np.loadtxt(csv, delimiter=",")
+    with g.ParticleFilter(1024, scene=g.Scene(scene), path=g.PATH_KD) as pf:
+        for f in range(1, 31):
+            p = pf.step(scans[f], f).pose
+            assert np.array_equal(bits(traj[f - 1, 1:4]), bits(list(p))), "frame %d" % f
+        kd = pf.get_kd()
+    assert "kd_nodes %d " % len(kd) in r.stdout, r.stdout
+    assert "kd_weight_sum %.0f" % float(kd[:, 7].copy().view(np.float32).astype(np.float64).sum()) in r.stdout, r.stdout

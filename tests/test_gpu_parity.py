@@ -253,3 +253,107 @@ def test_full_size_properties_65536(scans):
                 assert np.all(w == 1.0)
         ga = a.get_grid()
         assert ga.min() >= -113 and ga.max() <= 113 and np.array_equal(ga, b.get_grid())
+
+
+# ---- long horizons and the headline size, against the oracle (real datasets from data/_cache) -------------
+def _dataset(name):
+    sc = helpers.full_scans(name)
+    if sc is None:
+        pytest.skip("data/_cache/%s.scans.u16 is not on this box" % name)
+    return sc
+
+
+def test_free_running_2000_frames_train_lidar0():
+    """BASELINE configs[0]/[1] data: 2000 frames of train_lidar0 free-running at 4096 particles, engine vs
+    oracle: pose, extrema, Neff and the resample decision EVERY frame, the whole grid and particle cloud every
+    250 frames -- all bit for bit."""
+    g = _gpu()
+    scans = _dataset("train_lidar0")
+    n, frames = 4096, 2000
+    of = helpers.OracleFilter(n)
+    n_resampled = 0
+    with g.ParticleFilter(n) as pf:
+        for f in range(1, frames + 1):
+            r = pf.step(scans[f], f)
+            s = of.step_threaded(scans[f], f)
+            assert np.array_equal(bits(list(r.pose)), bits(list(s.robot))), "pose differs at frame %d" % f
+            assert (r.fit_min, r.fit_max, r.best_index, r.resampled) == (s.fit_min, s.fit_max, s.best, s.resampled), "frame %d" % f
+            assert np.array_equal(bits([r.sum_w, r.sum_w2, r.neff]), bits([s.sum_w, s.sum_w2, s.neff])), "frame %d" % f
+            n_resampled += r.resampled
+            if f % 250 == 0:
+                assert np.array_equal(pf.get_grid().reshape(-1), of.grid), "grid differs at frame %d" % f
+                x, y, th, w = pf.get_particles()
+                assert np.array_equal(bits(x), bits(of.x)) and np.array_equal(bits(y), bits(of.y))
+                assert np.array_equal(bits(th), bits(of.th)) and np.array_equal(bits(w), bits(of.w))
+        assert r.resample_count == n_resampled and n_resampled > 50
+    # the robot has actually moved and mapped something
+    assert abs(s.robot[0]) + abs(s.robot[1]) > 0.5 and (of.grid > 0).sum() > 2000
+    of.close()
+
+
+def test_headline_size_65536_against_oracle():
+    """BASELINE configs[1] size against the ORACLE (not scorer against scorer): 12 free-running frames of
+    train_lidar0 at 65 536 particles -- every particle's pose and weight, every grid byte, every frame's
+    extrema -- then a teacher-forced wide cloud (many beams off their windows, uncertain-pair queue under
+    load) scored against the oracle particle by particle."""
+    g = _gpu()
+    scans = _dataset("train_lidar0")
+    n = 65536
+    of = helpers.OracleFilter(n)
+    with g.ParticleFilter(n) as pf:
+        for f in range(1, 13):
+            r = pf.step(scans[f], f)
+            s = of.step_threaded(scans[f], f)
+            assert np.array_equal(bits(list(r.pose)), bits(list(s.robot))), "pose differs at frame %d" % f
+            assert (r.fit_min, r.fit_max, r.best_index, r.resampled) == (s.fit_min, s.fit_max, s.best, s.resampled), "frame %d" % f
+            assert np.array_equal(bits([r.sum_w, r.sum_w2, r.neff]), bits([s.sum_w, s.sum_w2, s.neff])), "frame %d" % f
+            x, y, th, w = pf.get_particles()
+            assert np.array_equal(bits(x), bits(of.x)) and np.array_equal(bits(y), bits(of.y)), "frame %d" % f
+            assert np.array_equal(bits(th), bits(of.th)) and np.array_equal(bits(w), bits(of.w)), "frame %d" % f
+        assert np.array_equal(pf.get_grid().reshape(-1), of.grid)
+        # teacher-forced: map after 1500 frames of the 4096-particle oracle run would be better still, but the
+        # dense pseudo-random grid makes every cell disagreement visible
+        grid = helpers.synth_grid(salt=43)
+        pf.set_grid(grid)
+        o = helpers.load_oracle()
+        for salt, spread, spread_th in ((3, 0.02, 0.01), (4, 0.6, 0.35), (5, 6.0, 3.0)):
+            x, y, th = helpers.synth_particles(n, salt=salt, spread=spread, spread_th=spread_th, center=(2.0, -3.0, 0.4))
+            pf.set_particles(x, y, th, np.ones(n, np.float32))
+            sc = np.ascontiguousarray(scans[700 + salt])
+            got = pf.score_particles(sc)
+            want = np.zeros(n, np.int32)
+            of.x[:], of.y[:], of.th[:] = x, y, th
+            of.grid[:] = grid
+            import threading
+            b = np.linspace(0, n, 33).astype(int)
+            def work(k):
+                a, e = int(b[k]), int(b[k + 1])
+                o.pfo_score2d_many(C.byref(of.cfg), P(grid, helpers.bp), P(x[a:e]), P(y[a:e]), P(th[a:e]), e - a, P(sc), P(want[a:e], helpers.ip))
+            ts = [threading.Thread(target=work, args=(k,)) for k in range(32)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            assert np.array_equal(got, want), "spread %g: %d of %d scores differ from the oracle" % (spread, (got != want).sum(), n)
+    of.close()
+
+
+def test_kd_free_running_400_frames_train_lidar3():
+    """BASELINE configs[2] data: the kd step free-running on train_lidar3 for 400 frames (four rebalances,
+    a tree of tens of thousands of nodes), engine vs oracle: pose / extrema / Neff / tree size every frame,
+    the whole tree node for node every 100 frames"""
+    g = _gpu()
+    scans = _dataset("train_lidar3")
+    n, frames = 256, 400
+    of = helpers.OracleKdFilter(n)
+    with g.ParticleFilter(n, path=g.PATH_KD) as pf:
+        for f in range(1, frames + 1):
+            r = pf.step(scans[f], f)
+            s = of.step(scans[f], f)
+            assert np.array_equal(bits(list(r.pose)), bits(list(s.robot))), "pose differs at frame %d" % f
+            assert r.kd_size == s.kd_size, "kd size differs at frame %d" % f
+            if f > 1:
+                assert (r.fit_min, r.fit_max, r.best_index, r.resampled) == (s.fit_min, s.fit_max, s.best, s.resampled), "frame %d" % f
+                assert np.array_equal(bits([r.neff]), bits([s.neff]))
+            if f % 100 == 0 or f in (5, 6):
+                assert np.array_equal(pf.get_kd(), of.tree), "tree differs at frame %d" % f
+        assert r.kd_size > 3000
+    of.close()

@@ -58,8 +58,10 @@ int main(int argc, char **argv)
     getPCData(&particles, &map, &kd, &nParticles, &nKD, pos);
     long occupied = 0, seen = 0;
     for (long i = 0; i < 1600L * 1600L; i++) { if (map[i] != -100) seen++; if (map[i] > 0) occupied++; }
-    printf("frames %d particles %d robotPos %.9g %.9g %.9g cells_seen %ld cells_occupied %ld\n", last, nParticles,
-           pos.x, pos.y, pos.z, seen, occupied);
+    double kd_w = 0.0;
+    for (int i = 0; i < nKD; i++) kd_w += kd[i].value.w;
+    printf("frames %d particles %d robotPos %.9g %.9g %.9g cells_seen %ld cells_occupied %ld kd_nodes %d kd_weight_sum %.0f\n", last, nParticles,
+           pos.x, pos.y, pos.z, seen, occupied, nKD, kd_w);
     if (csv) fclose(csv);
     particleFilterFree();
     return 0;
