@@ -454,11 +454,14 @@ k_kd_points_nn(const KdNode *__restrict__ tree, MapGeom g, const FrameResult *__
     nn[i] = ks->size > 0 ? kd_nn<false>(tree, px, py, 0.0f) : -1;
 }
 
-// kernel.cu:1350-1364 kernUpdateMapKD: w = clamp(w + val) when the point is within sqrt(2)*res of its
-// NN.  Saturating atomic (the reference's plain store races; same-sign updates commute).
+// kernel.cu:1350-1364 kernUpdateMapKD: w = clamp(w + val) when the point is within sqrt(2)*res of its NN.
+// The reference updates with a plain load and store from one thread per point, so points that share a
+// nearest node race: the colliding threads read the same old weight and store the same new one -- a node
+// moves by `val` ONCE per launch (pinned on the B200 against the reference's own kernel, T3).  Here the first
+// point to stamp the node's claim word with this (step, pass) applies the update; the others do nothing.
 __global__ void __launch_bounds__(128)
 k_kd_weights(KdNode *__restrict__ tree, MapGeom g, const KdState *__restrict__ ks, int cap, int pass,
-             const float2 *__restrict__ pts, const int *__restrict__ nn)
+             const float2 *__restrict__ pts, const int *__restrict__ nn, int *__restrict__ claim, int stamp)
 {
     if (ks->size <= 0) return;
     const int nW = min(ks->n_wall, cap), nF = min(min(ks->n_free, nW), cap);
@@ -470,15 +473,10 @@ k_kd_weights(KdNode *__restrict__ tree, MapGeom g, const KdState *__restrict__ k
     const int t = nn[i];
     const float2 p = pts[i];
     const KdNode nd = kd_load_cg(tree, t);
-    if (kd_dist(p.x, p.y, 0.0f, nd.x, nd.y, nd.z) < minDist) {
-        int *wp = reinterpret_cast<int *>(&tree[t].w);
-        int old = *wp, assumed;
-        do {
-            assumed = old;
-            float v = __fadd_rn(__int_as_float(assumed), val);
-            v = v < -(float)kClamp ? -(float)kClamp : v > (float)kClamp ? (float)kClamp : v;
-            old = atomicCAS(wp, assumed, __float_as_int(v));
-        } while (old != assumed);
+    if (kd_dist(p.x, p.y, 0.0f, nd.x, nd.y, nd.z) < minDist && atomicMax(&claim[t], stamp) < stamp) {
+        float v = __fadd_rn(nd.w, val);
+        v = v < -(float)kClamp ? -(float)kClamp : v > (float)kClamp ? (float)kClamp : v;
+        tree[t].w = v;
     }
 }
 

@@ -709,6 +709,10 @@ static int score_tiled_setup(int device)
     return per_sm > 0 && n_sm > 0 ? per_sm * n_sm : -1;
 }
 
+// the second-generation kernel (pf_score_staged.cuh) has the same signature
+typedef void (*StagedKernel)(const CUtensorMap, const int8_t *, MapGeom, const float *, const float *, const float *, int,
+                             const StepParams *, const float *, const TiledWork *, int *, int *);
+
 // returns the number of kernels launched, or -1.  partial: score_tiled_rows()*n ints.
 // With an auxiliary stream the wide/slow-beam kernel (k_score_fast) runs NEXT TO the tiled kernel
 // (fork after k_tile_prep, join before the row combine); inside a stream capture this becomes two
@@ -720,7 +724,8 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                               int *partial, int *counters, const Xchg &xc, int tiled_grid, cudaStream_t stream,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                               cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
-                              LapRec *laps = nullptr)
+                              LapRec *laps = nullptr, StagedKernel staged = nullptr, int staged_threads = 0, size_t staged_smem = 0,
+                              int staged_particles = 1024)
 {
     int nl = 4;
     if (!bounds_valid) {   // poses were not produced by k_motion this frame (test hooks): recompute
@@ -736,7 +741,11 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
     // one full wave; small filters get fewer blocks (an item is the smallest share)
     const int gt = min(tiled_grid, ((n + kTiledGroup - 1) / kTiledGroup) * kMaxChunks);
     if (ev0) cudaEventRecord(ev0, stream);
-    if (tiled_threads() == 512)
+    if (staged) {
+        // stage-major slices, one block per SM; small filters get fewer blocks (a few beams of one group each at least)
+        const int gs = min(tiled_grid, max(1, ((n + staged_particles - 1) / staged_particles) * 8));
+        launch_k(true, staged, dim3(gs), dim3(staged_threads), staged_smem, stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+    } else if (tiled_threads() == 512)
         launch_k(true, k_score_tiled<512, 2>, dim3(gt), dim3(512), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     else
         launch_k(true, k_score_tiled<256, 4>, dim3(gt), dim3(256), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);

@@ -18,6 +18,7 @@
 #include "pf_kernels2d.cuh"
 #include "pf_score_filtered.cuh"
 #include "pf_score_tiled.cuh"
+#include "pf_score_staged.cuh"
 #include "pf_kernels_kd.cuh"
 
 #include <algorithm>
@@ -75,6 +76,7 @@ struct pfslam_engine {
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
+    bool staged = true;            // scorer generation: k_score_staged (default) or k_score_tiled (PFSLAM_TILED_KERNEL=old)
     int tiled_grid = 0;            // k_score_tiled grid: SMs x resident blocks per SM
     // pinned host staging
     float *h_scan = nullptr;
@@ -90,6 +92,7 @@ struct pfslam_engine {
     int *bits_blk = nullptr; int n_bits_blk = 0;
     int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 4096;
     float2 *kd_pts = nullptr; int *kd_nn_idx = nullptr, *kd_ins_index = nullptr;
+    int *kd_claim = nullptr; int kd_stamp = 0;   // once-per-node-per-pass weight updates (k_kd_weights)
     bool kd_empty = true;                  // no tree yet (kdSize == 0, kernel.cu:1714)
     std::vector<KdNode> h_kd;
     // per-step parameters (device copy + pinned ring) and the captured step graph
@@ -198,7 +201,7 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
     cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->angle_cs); cudaFree(e->sp);
     cudaFree(e->kd); cudaFree(e->kds); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
-    cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index);
+    cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index); cudaFree(e->kd_claim);
     for (int r = 0; r < kMaxRanks; r++) if (e->peer_ipc[r] && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
     cudaFree(e->xreg);
     cudaFreeHost(e->h_sp);
@@ -303,6 +306,8 @@ static int engine_alloc(pfslam_engine *e)
         CUDA_TRY(cudaMalloc(&e->kd_pts, sizeof(float2) * 2 * e->pc_cap));
         CUDA_TRY(cudaMalloc(&e->kd_nn_idx, sizeof(int) * 2 * e->pc_cap));
         CUDA_TRY(cudaMalloc(&e->kd_ins_index, sizeof(int) * e->pc_cap));
+        CUDA_TRY(cudaMalloc(&e->kd_claim, sizeof(int) * (size_t)e->kd_cap));
+        CUDA_TRY(cudaMemsetAsync(e->kd_claim, 0, sizeof(int) * (size_t)e->kd_cap, e->stream));
     }
     CUDA_TRY(cudaMallocHost(&e->h_scan, sizeof(float) * e->cfg.n_beams));
     CUDA_TRY(cudaMallocHost(&e->h_res, sizeof(FrameResult)));
@@ -338,6 +343,8 @@ static int preload_kernels()
 #define PF_PRELOAD(k) CUDA_TRY(cudaFuncGetAttributes(&a, k))
     PF_PRELOAD(k_motion); PF_PRELOAD(k_cloud_bounds); PF_PRELOAD(k_bounds_reset); PF_PRELOAD(k_tile_prep);
     PF_PRELOAD(k_beam_prep); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<256, 4>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<512, 2>)); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
+    CUDA_TRY(cudaFuncGetAttributes(&a, k_score_staged<768, 4, kStageWindows>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_staged<1024, 2, kStageWindows>));
+    CUDA_TRY(cudaFuncGetAttributes(&a, k_score_staged<512, 4, kStageWindows>));
     PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
     PF_PRELOAD(k_score_kd<0>); PF_PRELOAD(k_score_kd<1>); PF_PRELOAD(k_score_kd<2>); PF_PRELOAD(k_kd_shadow<1>); PF_PRELOAD(k_kd_shadow<2>); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
@@ -405,6 +412,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
     if (ce != cudaSuccess) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "aux stream: %s", cudaGetErrorString(ce)); }
     { const char *no = getenv("PFSLAM_NO_OVERLAP"); e->overlap = !(no && atoi(no) != 0); }
+    { const char *tk = getenv("PFSLAM_TILED_KERNEL"); e->staged = !(tk && strcmp(tk, "old") == 0); }
     int rc = engine_alloc(e);
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
     if ((rc = preload_kernels()) != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
@@ -419,7 +427,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
         if (!fixed_ok) e->score_mode = PFSLAM_SCORE_EXACT;
         if (e->score_mode == PFSLAM_SCORE_TILED) {
             if (cfg->n_beams > kMaxGroups * kChunkBeams || make_grid_tensor_map(&e->tmap, e->grid, e->geom.w, e->geom.h) != 0 ||
-                (e->tiled_grid = score_tiled_setup(cfg->device)) <= 0)
+                (e->tiled_grid = (e->staged ? score_staged_setup(cfg->device) : score_tiled_setup(cfg->device))) <= 0)
                 e->score_mode = PFSLAM_SCORE_FILTERED;
         }
     }
@@ -606,7 +614,9 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
         int nl = score_tiled_launch(e->tmap, e->grid, e->geom, e->x, e->y, e->th, e->n, e->gidx0, scan, e->angle,
                                     e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
                                     e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->tiled_grid, e->stream, ev0, ev1,
-                                    use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr);
+                                    use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr,
+                                    e->staged ? staged_kernel() : nullptr, staged_threads(), sizeof(StagedSmem<kStageWindows>),
+                                    staged_threads() * (staged_threads() == 1024 ? 2 : 4));
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
@@ -935,8 +945,9 @@ static int kd_update_map(pfslam_engine *e)
             if (rc) return rc;
         }
     } else {
-        k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 0, e->kd_pts, e->kd_nn_idx);
-        k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 1, e->kd_pts, e->kd_nn_idx);
+        // claim stamps grow monotonically; node indices move at a rebuild, where stale stamps stay below every new one
+        k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 0, e->kd_pts, e->kd_nn_idx, e->kd_claim, ++e->kd_stamp);
+        k_kd_weights<<<ceil_div(e->pc_cap, 128), 128, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, 1, e->kd_pts, e->kd_nn_idx, e->kd_claim, ++e->kd_stamp);
         k_kd_insert<<<1, 1024, 0, e->stream>>>(e->kd, e->geom, e->ks, e->pc_cap, e->kd_cap, e->kd_pts, e->kd_nn_idx, e->kd_ins_index);
         e->launches += 3;
         // the tree size lives on the device: cover an upper bound (at most pc_cap inserts per frame)

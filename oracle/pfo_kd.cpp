@@ -272,9 +272,17 @@ void pfo_kd_update_map(pfo_kd_state *s, const float *scan)
             const std::vector<V4> &pc = pass == 0 ? freePC : wallPC;
             const std::vector<int> &ix = pass == 0 ? iF : iW;
             const float val = pass == 0 ? (float)PFO_FREE_WEIGHT : (float)PFO_OCCUPIED_WEIGHT;
+            /* kernUpdateMapKD (kernel.cu:1350-1364) updates tree[idx].value.w with a plain load and store from
+             * one thread per point.  Points that share a nearest node race: the colliding threads read the same
+             * old weight and store the same new one, so a node moves by `val` ONCE per launch however many
+             * points hit it.  That is what the reference's kernel does on the B200, repeatably (T3:
+             * tests/test_gpu_reference_cuda.py::test_kd_map_update_equals_reference); it is also the kd
+             * counterpart of the grid path's once-per-cell bool masks. */
+            std::vector<char> touched((size_t)s->kd_size, 0);
             for (size_t i = 0; i < ix.size(); i++) {
                 pfo_kdnode &t = s->tree[ix[i]];
-                if (dist3(pc[i].x, pc[i].y, pc[i].z, t.x, t.y, t.z) < minDist) {
+                if (dist3(pc[i].x, pc[i].y, pc[i].z, t.x, t.y, t.z) < minDist && !touched[ix[i]]) {
+                    touched[ix[i]] = 1;
                     float v = t.w + val;
                     t.w = v < -(float)PFO_CLAMP_VAL ? -(float)PFO_CLAMP_VAL : v > (float)PFO_CLAMP_VAL ? (float)PFO_CLAMP_VAL : v;
                 }
