@@ -76,6 +76,7 @@ struct FrameResult {
     int   kd_size, kd_ins;
     int   xchg_timeout;        // sharded engines: a peer-exchange wait ran into its time limit this frame
     int   resample_count;      // steps that resampled so far
+    int   wait_ext_ns, wait_tiles_ns;   // accumulated peer-exchange wait times (block 0 / the last block of k_weights_scan)
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
@@ -105,10 +106,16 @@ __device__ __forceinline__ float order_float(int k)
 __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
          const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds,
-         float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row)
+         float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row,
+         const float *__restrict__ scan_src, float *__restrict__ scan_dst, int n_beams)
 {
     __shared__ int s_b[6];
     pdl_trigger();                              // k_tile_prep's blocks may be staged now; they wait for this grid
+    // host API step (pfslam_step): the frame's scan is pulled from the pinned, device-mapped staging buffer by the
+    // first kernel of the step (nobody reads the device copy before this grid has completed), so the step graph needs
+    // no copy node for it
+    if (scan_src && blockIdx.x == gridDim.x - 1)
+        for (int j = threadIdx.x; j < n_beams; j += blockDim.x) scan_dst[j] = scan_src[j];
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +150,14 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
         if (threadIdx.x & 1) atomicMax(&bounds[threadIdx.x], s_b[threadIdx.x]);
         else atomicMin(&bounds[threadIdx.x], s_b[threadIdx.x]);
     }
+}
+
+// host API step: the frame result goes to the pinned, device-mapped result record from the last node of the graph
+__global__ void k_publish_result(const FrameResult *__restrict__ res, FrameResult *__restrict__ host_res)
+{
+    const int *s = reinterpret_cast<const int *>(res);
+    int *d = reinterpret_cast<int *>(host_res);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameResult) / 4); i += blockDim.x) d[i] = s[i];
 }
 
 __global__ void k_debug_trig(const float *__restrict__ x, long long n, float *__restrict__ c,
@@ -258,13 +273,13 @@ k_extrema(const int *__restrict__ blk_min, const long long *__restrict__ blk_max
 
 // combine the per-rank extrema: global min, max, first arg-max and its pose
 __device__ __forceinline__ void reduce_extrema(const Extrema *__restrict__ all, int n_ranks,
-                                               int &gmin, int &gmax, int &best, float pose[3])
+                                               int &gmin, int &gmax, int &best, float pose[3], bool wire)
 {
-    Extrema b = xc_load_extrema(all);
+    Extrema b = xc_load_extrema(all, wire);
     gmin = b.fit_min;
     long long mk = extrema_key(b.fit_max, b.best_gidx);
     for (int r = 1; r < n_ranks; r++) {
-        const Extrema e = xc_load_extrema(all + r);
+        const Extrema e = xc_load_extrema(all + r, wire);
         gmin = min(gmin, e.fit_min);
         long long t = extrema_key(e.fit_max, e.best_gidx);
         if (t > mk) { mk = t; b = e; }
@@ -341,13 +356,17 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
     const int seq = sp->seq;
     if (xc.parity_mask) {
         if (threadIdx.x < 32) {
+            const unsigned long long t0 = xc_now_ns();
             const bool ok = xc_wait_warp(xc, kXcExt, seq);
-            if (!ok && blockIdx.x == 0 && threadIdx.x == 0) res->xchg_timeout = 1;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (!ok) res->xchg_timeout = 1;
+                res->wait_ext_ns += (int)(xc_now_ns() - t0);
+            }
         }
         __syncthreads();
     }
     int gmin, gmax, best; float pose[3];
-    reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose);
+    reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose, xc.parity_mask != 0);
     const int rng = gmax - gmin;
     const float c = rng > 0 ? __fdiv_rn(1.0f, (float)rng) : 1.0f;
     const float fmin = (float)gmin;
@@ -397,8 +416,12 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         if (threadIdx.x == 0) { *done_counter = 0; xc_signal(xc, kXcTiles, seq); }
         if (!fuse_prefix) return;
         if (threadIdx.x < 32) {
+            const unsigned long long t0 = xc_now_ns();
             const bool ok = xc_wait_warp(xc, kXcTiles, seq);
-            if (!ok && threadIdx.x == 0) res->xchg_timeout = 1;
+            if (threadIdx.x == 0) {
+                if (!ok) res->xchg_timeout = 1;
+                res->wait_tiles_ns += (int)(xc_now_ns() - t0);
+            }
         }
         __syncthreads();
     } else {
@@ -416,14 +439,22 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         }
     }
     __syncthreads();
+    // the two sequential chains (sum of w in global tile order = the CDF's tile prefix, sum of w^2) run in two
+    // warps side by side, in place in shared memory; the prefix goes out to global memory in parallel afterwards
+    __shared__ float s_tot[2];
     if (threadIdx.x == 0) {
-        float p = 0.0f, p2 = 0.0f;
-        prefix[0] = 0.0f;
-        for (int t = 0; t < nt; t++) {
-            p = __fadd_rn(p, s_t[t]);
-            p2 = __fadd_rn(p2, s_t[nt + t]);
-            prefix[t + 1] = p;
-        }
+        float p = 0.0f;
+        for (int t = 0; t < nt; t++) { p = __fadd_rn(p, s_t[t]); s_t[t] = p; }
+        s_tot[0] = p;
+    } else if (threadIdx.x == 32) {
+        float p2 = 0.0f;
+        for (int t = 0; t < nt; t++) p2 = __fadd_rn(p2, s_t[nt + t]);
+        s_tot[1] = p2;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t <= nt; t += blockDim.x) prefix[t] = t ? s_t[t - 1] : 0.0f;
+    if (threadIdx.x == 0) {
+        const float p = s_tot[0], p2 = s_tot[1];
         const float neff = __fdiv_rn(__fmul_rn(p, p), p2);
         if (write_pose) { res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2]; }
         res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
@@ -458,17 +489,23 @@ k_prefix(const Xchg xc, const StepParams *__restrict__ sp, int n_tiles_local, in
         s_t[nt + t] = __ldcg(&blk[n_tiles_local + tl]);
     }
     __syncthreads();
+    __shared__ float s_tot[2];
     if (threadIdx.x == 0) {
-        float p = 0.0f, p2 = 0.0f;
-        prefix[0] = 0.0f;
-        for (int t = 0; t < nt; t++) {
-            p = __fadd_rn(p, s_t[t]);
-            p2 = __fadd_rn(p2, s_t[nt + t]);
-            prefix[t + 1] = p;
-        }
+        float p = 0.0f;
+        for (int t = 0; t < nt; t++) { p = __fadd_rn(p, s_t[t]); s_t[t] = p; }
+        s_tot[0] = p;
+    } else if (threadIdx.x == 32) {
+        float p2 = 0.0f;
+        for (int t = 0; t < nt; t++) p2 = __fadd_rn(p2, s_t[nt + t]);
+        s_tot[1] = p2;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t <= nt; t += blockDim.x) prefix[t] = t ? s_t[t - 1] : 0.0f;
+    if (threadIdx.x == 0) {
+        const float p = s_tot[0], p2 = s_tot[1];
         float neff = __fdiv_rn(__fmul_rn(p, p), p2);
         int gmin, gmax, best; float pose[3];
-        reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose);
+        reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose, xc.parity_mask != 0);
         if (write_pose) { res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2]; }
         res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
         res->sum_w = p; res->sum_w2 = p2; res->neff = neff;
@@ -565,7 +602,7 @@ __device__ __forceinline__ void map_pose(const FrameResult *__restrict__ res, co
 {
     if (pose_from_ext) {
         int gmin, gmax, best;
-        reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose);
+        reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose, xc.parity_mask != 0);
     } else {
         pose[0] = res->pose[0]; pose[1] = res->pose[1]; pose[2] = res->pose[2];
     }

@@ -332,7 +332,7 @@ k_icp(const KdNode *__restrict__ tree, const Xchg xc,
         const float t_x = __fsub_rn(s_m[2], __fmaf_rn(cs, s_m[0], -__fmul_rn(sn, s_m[1])));
         const float t_y = __fsub_rn(s_m[3], __fmaf_rn(sn, s_m[0], __fmul_rn(cs, s_m[1])));
         int gmin, gmax, best; float pose[3];
-        reduce_extrema(xc_ext(xc, sp->seq), xc.n_ranks, gmin, gmax, best, pose);   // k_weights_scan already waited for it
+        reduce_extrema(xc_ext(xc, sp->seq), xc.n_ranks, gmin, gmax, best, pose, xc.parity_mask != 0);   // k_weights_scan already waited for it
         res->pose[0] = __fadd_rn(pose[0], t_x);
         res->pose[1] = __fadd_rn(pose[1], t_y);
         res->pose[2] = __fadd_rn(pose[2], pf_asinf(sn));
@@ -455,10 +455,11 @@ k_kd_points_nn(const KdNode *__restrict__ tree, MapGeom g, const FrameResult *__
 }
 
 // kernel.cu:1350-1364 kernUpdateMapKD: w = clamp(w + val) when the point is within sqrt(2)*res of its NN.
-// The reference updates with a plain load and store from one thread per point, so points that share a
-// nearest node race: the colliding threads read the same old weight and store the same new one -- a node
-// moves by `val` ONCE per launch (pinned on the B200 against the reference's own kernel, T3).  Here the first
-// point to stamp the node's claim word with this (step, pass) applies the update; the others do nothing.
+// The reference updates with a plain load and store from one thread per point, so points that share a nearest
+// node race: of k colliding threads any number between 1 and k takes effect (the B200 shows both collapsing and
+// accumulating collisions on one frame, T3).  The engine defines the deterministic outcome "once per node per
+// launch" -- always one of the race's legal results, and the kd counterpart of the grid path's once-per-cell
+// bool masks: the first point to stamp the node's claim word with this (step, pass) applies the update.
 __global__ void __launch_bounds__(128)
 k_kd_weights(KdNode *__restrict__ tree, MapGeom g, const KdState *__restrict__ ks, int cap, int pass,
              const float2 *__restrict__ pts, const int *__restrict__ nn, int *__restrict__ claim, int stamp)

@@ -61,15 +61,29 @@ __device__ __forceinline__ unsigned long long xc_now_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ int xc_ld_acquire(const int *p)
+// Flags are polled with relaxed system-scope loads (an acquire load per poll would cost a fence per poll) and
+// the consumer fences ONCE after the flag has arrived; producers fence once and then raise every peer's flag
+// with relaxed stores (a release store per peer would repeat the fence -- one NVLink round trip -- per peer,
+// which is what made the exchange cost grow with the rank count).
+__device__ __forceinline__ int xc_ld_relaxed(const int *p)
 {
     int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void xc_st_release(int *p, int v)
+__device__ __forceinline__ void xc_st_relaxed(int *p, int v)
 {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 xc_ld_relaxed16(const int4 *p)
+{
+    int4 v;
+    asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void xc_st_relaxed16(int4 *p, int4 v)
+{
+    asm volatile("st.relaxed.sys.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ Extrema *xc_ext(const Xchg &xc, int seq)
@@ -84,53 +98,69 @@ __device__ __forceinline__ float *xc_tiles(const Xchg &xc, int seq)
 // A whole warp (all 32 lanes call it) waits until every rank's flag of `kind` has reached this step's
 // sequence number: lane r polls rank r's flag, so the wait costs one round of latency whatever the rank
 // count.  Returns false on timeout (the caller records it in the frame result; nothing hangs).
+// kXcExt has no flag word: in a peer region the extrema record travels as two self-validating 16-byte halves
+// {min, max, arg-max index, seq} and {x, y, theta, seq}; each half is one store, so a half that shows this
+// step's number is complete, and no fence is needed on either side.
 __device__ __forceinline__ bool xc_wait_warp(const Xchg &xc, int kind, int seq)
 {
     if (!xc.parity_mask) return true;
     const int lane = threadIdx.x & 31;
-    const int *f = xc.flags + kind * kMaxRanks;
     const unsigned long long t0 = xc_now_ns();
     const unsigned long long limit = (unsigned long long)xc.timeout_ms * 1000000ull;
     bool ok = true;
     if (lane < xc.n_ranks) {
         unsigned spins = 0;
-        while (xc_ld_acquire(f + lane) - seq < 0) {
-            if ((++spins & 255u) == 0u && xc_now_ns() - t0 > limit) { ok = false; break; }
+        if (kind == kXcExt) {
+            const int4 *rec = reinterpret_cast<const int4 *>(xc.ext_all + (seq & 1) * kMaxRanks + lane);
+            for (;;) {
+                const int4 a = xc_ld_relaxed16(rec), b = xc_ld_relaxed16(rec + 1);
+                if (a.w == seq && b.w == seq) break;
+                if ((++spins & 255u) == 0u && xc_now_ns() - t0 > limit) { ok = false; break; }
+            }
+        } else {
+            const int *f = xc.flags + kind * kMaxRanks;
+            while (xc_ld_relaxed(f + lane) - seq < 0) {
+                if ((++spins & 255u) == 0u && xc_now_ns() - t0 > limit) { ok = false; break; }
+            }
         }
     }
+    if (kind != kXcExt) __threadfence_system();   // acquire: what the producers wrote before their flags is visible now
     return __all_sync(0xffffffffu, ok);
 }
 
 // One thread, after the data stores (and a block barrier if other threads made them): make the
-// stores visible system-wide, then raise this rank's flag in every peer's region.
+// stores visible system-wide ONCE, then raise this rank's flag in every peer's region.
 __device__ __forceinline__ void xc_signal(const Xchg &xc, int kind, int seq)
 {
     __threadfence_system();
     for (int r = 0; r < xc.n_ranks; r++)
-        xc_st_release(reinterpret_cast<int *>(xc.peer[r] + xc.off_flags) + kind * kMaxRanks + xc.rank, seq);
+        xc_st_relaxed(reinterpret_cast<int *>(xc.peer[r] + xc.off_flags) + kind * kMaxRanks + xc.rank, seq);
 }
 
-// Extrema of this shard -> ext_local (local modes) or slot [parity][rank] of every peer's region.
+// Extrema of this shard -> ext_local (local modes) or slot [parity][rank] of every peer's region (wire format,
+// see xc_wait_warp): 2 stores per peer, no fence, no flag.
 __device__ __forceinline__ void xc_publish_extrema(const Xchg &xc, Extrema *ext_local, const Extrema &e, int seq)
 {
     if (!xc.parity_mask) { *ext_local = e; return; }
-    const int4 a = make_int4(e.fit_min, e.fit_max, e.best_gidx, __float_as_int(e.x));
-    const int4 b = make_int4(__float_as_int(e.y), __float_as_int(e.th), 0, 0);
+    const int4 a = make_int4(e.fit_min, e.fit_max, e.best_gidx, seq);
+    const int4 b = make_int4(__float_as_int(e.x), __float_as_int(e.y), __float_as_int(e.th), seq);
     for (int r = 0; r < xc.n_ranks; r++) {
         int4 *dst = reinterpret_cast<int4 *>(reinterpret_cast<Extrema *>(xc.peer[r] + xc.off_ext) +
                                              (seq & 1) * kMaxRanks + xc.rank);
-        dst[0] = a; dst[1] = b;
+        xc_st_relaxed16(dst, a);
+        xc_st_relaxed16(dst + 1, b);
     }
-    xc_signal(xc, kXcExt, seq);
 }
 
-__device__ __forceinline__ Extrema xc_load_extrema(const Extrema *p)
+// wire: the record sits in a peer region (two stamped halves), else it is a plain Extrema
+__device__ __forceinline__ Extrema xc_load_extrema(const Extrema *p, bool wire)
 {
     const int4 a = __ldcg(reinterpret_cast<const int4 *>(p));
     const int4 b = __ldcg(reinterpret_cast<const int4 *>(p) + 1);
     Extrema e;
-    e.fit_min = a.x; e.fit_max = a.y; e.best_gidx = a.z; e.x = __int_as_float(a.w);
-    e.y = __int_as_float(b.x); e.th = __int_as_float(b.y); e.pad0 = 0; e.pad1 = 0;
+    e.fit_min = a.x; e.fit_max = a.y; e.best_gidx = a.z; e.pad0 = 0; e.pad1 = 0;
+    if (wire) { e.x = __int_as_float(b.x); e.y = __int_as_float(b.y); e.th = __int_as_float(b.z); }
+    else { e.x = __int_as_float(a.w); e.y = __int_as_float(b.x); e.th = __int_as_float(b.y); }
     return e;
 }
 

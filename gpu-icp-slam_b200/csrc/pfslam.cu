@@ -79,8 +79,9 @@ struct pfslam_engine {
     bool staged = true;            // scorer generation: k_score_staged (default) or k_score_tiled (PFSLAM_TILED_KERNEL=old)
     int tiled_grid = 0;            // k_score_tiled grid: SMs x resident blocks per SM
     // pinned host staging
-    float *h_scan = nullptr;
-    FrameResult *h_res = nullptr;
+    float *h_scan = nullptr, *h_scan_dev = nullptr;     // pinned + mapped: host pointer, device alias
+    FrameResult *h_res = nullptr, *h_res_dev = nullptr;
+    bool io_capture = false;               // capturing the host-API flavour of the step graph
     long long launches = 0;
     // kd-tree point-cloud path
     KdNode *kd = nullptr; int kd_cap = 0;
@@ -104,9 +105,14 @@ struct pfslam_engine {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraphNode_t graph_param_node = nullptr;
+    // the same step with the host API's copies inside: scan H2D from the pinned staging buffer at the head,
+    // frame result D2H into pinned memory at the tail (pfslam_step = one launch + one synchronisation)
+    cudaGraph_t graph_io = nullptr;
+    cudaGraphExec_t graph_io_exec = nullptr;
+    cudaGraphNode_t graph_io_param_node = nullptr;
     bool graph_failed = false;
     bool use_graph = true;
-    int graph_kernels = 0;
+    int graph_kernels = 0, graph_io_kernels = 0;
     bool in_capture = false;
     bool external_params = false;
     // shard exchange (pf_xchg.cuh): xc_host = single GPU / host-run collectives, xc_p2p = peer memory
@@ -208,6 +214,8 @@ int pfslam_destroy(pfslam_engine *e)
     for (auto ev : e->lap_ev) if (ev) cudaEventDestroy(ev);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->graph) cudaGraphDestroy(e->graph);
+    if (e->graph_io_exec) cudaGraphExecDestroy(e->graph_io_exec);
+    if (e->graph_io) cudaGraphDestroy(e->graph_io);
     cudaFreeHost(e->h_scan); cudaFreeHost(e->h_res);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     for (auto ev : e->laps.ev) cudaEventDestroy(ev);
@@ -309,8 +317,10 @@ static int engine_alloc(pfslam_engine *e)
         CUDA_TRY(cudaMalloc(&e->kd_claim, sizeof(int) * (size_t)e->kd_cap));
         CUDA_TRY(cudaMemsetAsync(e->kd_claim, 0, sizeof(int) * (size_t)e->kd_cap, e->stream));
     }
-    CUDA_TRY(cudaMallocHost(&e->h_scan, sizeof(float) * e->cfg.n_beams));
-    CUDA_TRY(cudaMallocHost(&e->h_res, sizeof(FrameResult)));
+    CUDA_TRY(cudaHostAlloc(&e->h_scan, sizeof(float) * e->cfg.n_beams, cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&e->h_res, sizeof(FrameResult), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer(&e->h_scan_dev, e->h_scan, 0));
+    CUDA_TRY(cudaHostGetDevicePointer(&e->h_res_dev, e->h_res, 0));
     // initial state: kernel.cu:122-132
     CUDA_TRY(cudaMemsetAsync(e->x, 0, sizeof(float) * 3 * n, e->stream));
     std::vector<float> ones(n, 1.0f);
@@ -343,13 +353,12 @@ static int preload_kernels()
 #define PF_PRELOAD(k) CUDA_TRY(cudaFuncGetAttributes(&a, k))
     PF_PRELOAD(k_motion); PF_PRELOAD(k_cloud_bounds); PF_PRELOAD(k_bounds_reset); PF_PRELOAD(k_tile_prep);
     PF_PRELOAD(k_beam_prep); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<256, 4>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<512, 2>)); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
-    CUDA_TRY(cudaFuncGetAttributes(&a, k_score_staged<768, 4, kStageWindows>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_staged<1024, 2, kStageWindows>));
-    CUDA_TRY(cudaFuncGetAttributes(&a, k_score_staged<512, 4, kStageWindows>));
+    CUDA_TRY(cudaFuncGetAttributes(&a, staged_kernel()));
     PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
     PF_PRELOAD(k_score_kd<0>); PF_PRELOAD(k_score_kd<1>); PF_PRELOAD(k_score_kd<2>); PF_PRELOAD(k_kd_shadow<1>); PF_PRELOAD(k_kd_shadow<2>); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
     PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
-    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait);
+    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait); PF_PRELOAD(k_publish_result);
 #undef PF_PRELOAD
     return PFSLAM_OK;
 }
@@ -413,6 +422,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     if (ce != cudaSuccess) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "aux stream: %s", cudaGetErrorString(ce)); }
     { const char *no = getenv("PFSLAM_NO_OVERLAP"); e->overlap = !(no && atoi(no) != 0); }
     { const char *tk = getenv("PFSLAM_TILED_KERNEL"); e->staged = !(tk && strcmp(tk, "old") == 0); }
+    { const char *dg = getenv("PFSLAM_STAGED_DEBUG"); const int v = dg ? atoi(dg) : 0; cudaMemcpyToSymbol(g_staged_dbg, &v, sizeof v); }
     int rc = engine_alloc(e);
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
     if ((rc = preload_kernels()) != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
@@ -547,6 +557,8 @@ int pfslam_exchange_ready(pfslam_engine *e)
     }
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    if (e->graph_io_exec) { cudaGraphExecDestroy(e->graph_io_exec); e->graph_io_exec = nullptr; }
+    if (e->graph_io) { cudaGraphDestroy(e->graph_io); e->graph_io = nullptr; }
     e->graph_failed = false;
     e->p2p_ready = true;
     return PFSLAM_OK;
@@ -578,7 +590,8 @@ static int ph_motion(pfslam_engine *e, int32_t frame)
     const Xchg &xc = *e->cur_xc;
     // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
     k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
-                                                         xc.snap, xc.snap_stride, xc.parity_mask, xc.snap_aos, e->score_partial);
+                                                         xc.snap, xc.snap_stride, xc.parity_mask, xc.snap_aos, e->score_partial,
+                                                         e->io_capture ? e->h_scan_dev : nullptr, e->scan, e->cfg.n_beams);
     if (e->laps_on) e->laps.mark(e->stream, kLapMotion);
     e->bounds_valid = true;
     e->launches++;
@@ -1021,14 +1034,15 @@ static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
 
 // Capture the whole single-GPU step once; every later step is one cudaGraphLaunch whose head node
 // copies that step's {scan pointer, frame} from a pinned slot into the device StepParams.
-static int build_graph(pfslam_engine *e)
+static int build_graph(pfslam_engine *e, bool with_io)
 {
     const long long launches_before = e->launches;
     if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return -1; }
     cudaMemcpyAsync(e->sp, &e->h_sp[0], sizeof(StepParams), cudaMemcpyHostToDevice, e->stream);
-    e->in_capture = true;
+    e->in_capture = true; e->io_capture = with_io;       // with_io: k_motion pulls the scan from the mapped staging buffer
     int rc = run_phases(e, nullptr, 0);
-    e->in_capture = false;
+    e->in_capture = false; e->io_capture = false;
+    if (with_io) k_publish_result<<<1, 32, 0, e->stream>>>(e->res, e->h_res_dev);
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     e->launches = launches_before;
@@ -1051,9 +1065,28 @@ static int build_graph(pfslam_engine *e)
     if (!pn) { cudaGraphDestroy(g); return -1; }
     cudaGraphExec_t ge = nullptr;
     if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); return -1; }
-    e->graph = g; e->graph_exec = ge; e->graph_param_node = pn;
-    e->graph_kernels = n_kernels;
+    if (with_io) { e->graph_io = g; e->graph_io_exec = ge; e->graph_io_param_node = pn; e->graph_io_kernels = n_kernels; }
+    else { e->graph = g; e->graph_exec = ge; e->graph_param_node = pn; e->graph_kernels = n_kernels; }
     return 0;
+}
+
+static bool graph_usable(const pfslam_engine *e)
+{
+    return e->use_graph && !e->prof_on && !e->laps_on && !e->graph_failed && e->cfg.path == PFSLAM_PATH_GRID2D;
+}
+
+// one replay of a captured step with this frame's {scan pointer, frame, seq} in its head copy node
+static int launch_graph(pfslam_engine *e, cudaGraphExec_t ge, cudaGraphNode_t pn, const float *scan, int32_t frame)
+{
+    StepParams *slot = nullptr;
+    int rc = next_param_slot(e, &slot);
+    if (rc) return rc;
+    slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
+    CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ge, pn, e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaGraphLaunch(ge, e->stream));
+    e->cur = *slot;
+    e->launches += ge == e->graph_io_exec ? e->graph_io_kernels : e->graph_kernels;
+    return param_slot_used(e);
 }
 
 int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
@@ -1067,20 +1100,9 @@ int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
     e->seq++;
     if (e->cfg.path == PFSLAM_PATH_KD) return kd_step(e, scan_dev, frame);
     const float *scan = scan_dev ? scan_dev : e->scan;
-    if (e->use_graph && !e->prof_on && !e->laps_on && !e->graph_failed) {
-        if (!e->graph_exec && build_graph(e) != 0) e->graph_failed = true;
-        if (e->graph_exec) {
-            StepParams *slot = nullptr;
-            int rc = next_param_slot(e, &slot);
-            if (rc) return rc;
-            slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
-            CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(e->graph_exec, e->graph_param_node, e->sp, slot,
-                                                        sizeof(StepParams), cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaGraphLaunch(e->graph_exec, e->stream));
-            e->cur = *slot;
-            e->launches += e->graph_kernels;
-            return param_slot_used(e);
-        }
+    if (graph_usable(e)) {
+        if (!e->graph_exec && build_graph(e, false) != 0) e->graph_failed = true;
+        if (e->graph_exec) return launch_graph(e, e->graph_exec, e->graph_param_node, scan, frame);
     }
     // plain launches (profiling, or graph capture unavailable on this stream)
     int rc = push_params(e, scan, frame);
@@ -1098,6 +1120,7 @@ static void copy_result(const FrameResult *r, pfslam_frame_result *out)
     out->kd_size = r->kd_size; out->kd_inserted = r->kd_ins;
     out->exchange_timeout = r->xchg_timeout;
     out->resample_count = r->resample_count;
+    out->wait_extrema_ns = r->wait_ext_ns; out->wait_tiles_ns = r->wait_tiles_ns;
 }
 
 int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
@@ -1115,9 +1138,28 @@ int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
 int pfslam_step(pfslam_engine *e, const float *scan, int32_t frame, pfslam_frame_result *out)
 {
     int rc;
+    if (!e || !scan) return set_error(PFSLAM_ERR_ARG, "null argument");
+    pfslam_frame_result tmp;
+    if (graph_usable(e) && (e->n_ranks == 1 || e->p2p_ready)) {
+        // host scan in, host result out: one graph launch (copies inside) and one synchronisation
+        CUDA_TRY(cudaSetDevice(e->cfg.device));
+        // earlier asynchronous work (pfslam_step_async, phase calls) may still be reading the staging buffers
+        if (cudaStreamQuery(e->stream) != cudaSuccess) { cudaGetLastError(); CUDA_TRY(cudaStreamSynchronize(e->stream)); }
+        e->cur_xc = e->p2p_ready ? &e->xc_p2p : &e->xc_host;      // before the capture: the kernels take it by value
+        if (!e->graph_io_exec && build_graph(e, true) != 0) e->graph_failed = true;
+        if (e->graph_io_exec) {
+            memcpy(e->h_scan, scan, sizeof(float) * e->cfg.n_beams);
+            e->seq++;
+            if ((rc = launch_graph(e, e->graph_io_exec, e->graph_io_param_node, e->scan, frame))) return rc;
+            CUDA_TRY(cudaStreamSynchronize(e->stream));
+            copy_result(e->h_res, out ? out : &tmp);
+            if (e->h_res->xchg_timeout)
+                return set_error(PFSLAM_ERR_STATE, "peer exchange timed out (a shard stopped stepping, or the shards are out of step)");
+            return PFSLAM_OK;
+        }
+    }
     if ((rc = pfslam_upload_scan(e, scan))) return rc;
     if ((rc = pfslam_step_async(e, nullptr, frame))) return rc;
-    pfslam_frame_result tmp;
     if ((rc = pfslam_fetch_result(e, out ? out : &tmp))) return rc;
     return PFSLAM_OK;
 }

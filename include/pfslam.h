@@ -76,6 +76,8 @@ typedef struct pfslam_frame_result {
     int32_t kd_inserted;         /* kd path: nodes inserted this frame */
     int32_t exchange_timeout;    /* sharded engines: 1 once a peer-exchange wait hit its time limit (results invalid) */
     int32_t resample_count;      /* steps that resampled so far (reset by the explicit-pose test entry points) */
+    int32_t wait_extrema_ns;     /* sharded engines: time this rank's step kernels have spent waiting for the peers' */
+    int32_t wait_tiles_ns;       /*   extrema / tile sums so far (nanoseconds, accumulated; wraps after ~2 s of waiting) */
 } pfslam_frame_result;
 
 /* ---- life cycle: particleFilterInit(Scene*) / particleFilterFree(), kernel.cu:107-178 ---- */

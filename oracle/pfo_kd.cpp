@@ -239,8 +239,12 @@ void pfo_kd_destroy_state(pfo_kd_state *s)
 
 static inline float round_frac(float a, float frac) { return roundf(a / frac) * frac; }   /* kernel.cu:52 */
 
-/* kernel.cu:1406-1540 PFUpdateMapKD */
-void pfo_kd_update_map(pfo_kd_state *s, const float *scan)
+/* kernel.cu:1406-1540 PFUpdateMapKD; hits_free / hits_wall (optional, kd_size ints each, zeroed by the caller):
+ * points within range per node in the free / wall weight pass */
+void pfo_kd_update_map_hits(pfo_kd_state *s, const float *scan, int *hits_free, int *hits_wall);
+void pfo_kd_update_map(pfo_kd_state *s, const float *scan) { pfo_kd_update_map_hits(s, scan, NULL, NULL); }
+
+void pfo_kd_update_map_hits(pfo_kd_state *s, const float *scan, int *hits_free, int *hits_wall)
 {
     const pfo_config *c = &s->cfg;
     const size_t nc = (size_t)c->map_w * c->map_h;
@@ -273,15 +277,22 @@ void pfo_kd_update_map(pfo_kd_state *s, const float *scan)
             const std::vector<int> &ix = pass == 0 ? iF : iW;
             const float val = pass == 0 ? (float)PFO_FREE_WEIGHT : (float)PFO_OCCUPIED_WEIGHT;
             /* kernUpdateMapKD (kernel.cu:1350-1364) updates tree[idx].value.w with a plain load and store from
-             * one thread per point.  Points that share a nearest node race: the colliding threads read the same
-             * old weight and store the same new one, so a node moves by `val` ONCE per launch however many
-             * points hit it.  That is what the reference's kernel does on the B200, repeatably (T3:
-             * tests/test_gpu_reference_cuda.py::test_kd_map_update_equals_reference); it is also the kd
-             * counterpart of the grid path's once-per-cell bool masks. */
+             * one thread per point.  Points that share a nearest node therefore RACE in the reference: of k
+             * colliding threads, any number between 1 and k may take effect, depending on which of them read
+             * the weight before the others stored it (lanes of one warp always collapse to one; warps that
+             * overlap in time collapse, warps that do not accumulate).  On the B200 the reference's kernel
+             * shows both outcomes on the same frame (T3, test_kd_map_update_equals_reference).  The engine and
+             * this oracle define the deterministic outcome "ONCE per node per launch" -- always one of the
+             * race's legal results, and the kd counterpart of the grid path's once-per-cell bool masks
+             * (kernel.cu:513-522).  `hits` (optional) receives the number of colliding points per node so
+             * that a test can check the reference's value against the legal range. */
             std::vector<char> touched((size_t)s->kd_size, 0);
+            int *hits = pass == 0 ? hits_free : hits_wall;
             for (size_t i = 0; i < ix.size(); i++) {
                 pfo_kdnode &t = s->tree[ix[i]];
-                if (dist3(pc[i].x, pc[i].y, pc[i].z, t.x, t.y, t.z) < minDist && !touched[ix[i]]) {
+                if (dist3(pc[i].x, pc[i].y, pc[i].z, t.x, t.y, t.z) < minDist) {
+                    if (hits) hits[ix[i]]++;
+                    if (touched[ix[i]]) continue;
                     touched[ix[i]] = 1;
                     float v = t.w + val;
                     t.w = v < -(float)PFO_CLAMP_VAL ? -(float)PFO_CLAMP_VAL : v > (float)PFO_CLAMP_VAL ? (float)PFO_CLAMP_VAL : v;

@@ -253,6 +253,7 @@ def load_oracle_kd():
     o.pfo_kd_destroy_state.argtypes = [C.POINTER(OKdState)]
     o.pfo_kd_step.argtypes = [C.POINTER(OKdState), fp, C.c_int]
     o.pfo_kd_update_map.argtypes = [C.POINTER(OKdState), fp]
+    o.pfo_kd_update_map_hits.argtypes = [C.POINTER(OKdState), fp, ip, ip]
     o._kd_typed = True
     return o
 

@@ -310,8 +310,9 @@ def test_kd_icp_matches_reference(t3kd, scans):
     assert worst[0] < 2e-4 and worst[1] < 2e-4 and worst[2] < 1e-4, "worst |engine - reference| = %r" % (worst,)
 
 
-def _oracle_update_map(tree, robot, scan, kd_cap=1 << 18):
-    """pfo_kd_update_map on a given tree and robotPos; returns the tree afterwards"""
+def _oracle_update_map(tree, robot, scan, kd_cap=1 << 18, with_hits=False):
+    """pfo_kd_update_map on a given tree and robotPos; returns the tree afterwards (and, with_hits, the number of
+    points in range per node in the free and the wall weight pass)"""
     of = helpers.OracleKdFilter(8, kd_cap=kd_cap)
     s = of.s.contents
     if len(tree):
@@ -319,10 +320,15 @@ def _oracle_update_map(tree, robot, scan, kd_cap=1 << 18):
     s.kd_size = len(tree)
     s.robot[0], s.robot[1], s.robot[2] = float(robot[0]), float(robot[1]), float(robot[2])
     sc = np.ascontiguousarray(scan, np.float32)
-    of.o.pfo_kd_update_map(of.s, P(sc))
+    hf, hw = np.zeros(max(len(tree), 1), np.int32), np.zeros(max(len(tree), 1), np.int32)
+    of.o.pfo_kd_update_map_hits(of.s, P(sc), P(hf, helpers.ip), P(hw, helpers.ip))
     out = of.tree.copy()
     of.close()
-    return out
+    return (out, hf, hw) if with_hits else out
+
+
+def _clamp113(v):
+    return np.clip(v, -113.0, 113.0)
 
 
 def test_kd_first_scan_build_equals_reference(t3kd, scans):
@@ -345,17 +351,22 @@ def test_kd_first_scan_build_equals_reference(t3kd, scans):
 @pytest.mark.parametrize("n_frames", [3, 50, 104])
 def test_kd_map_update_equals_reference(t3kd, scans, n_frames):
     """PFUpdateMapKD on the B200 (kernGetWalls masks, host point lists, findCorrespondenceIndexKD x2,
-    kernUpdateMapKD x2, kernTestCorrespondance, sequential KDTree::InsertNode) == the engine's device-side map
-    update == the oracle: every node (links, coordinates, weights), over consecutive frames at the robot's
-    pose and at offset poses"""
+    kernUpdateMapKD x2, kernTestCorrespondance, sequential KDTree::InsertNode) against the engine's device-side
+    map update and the oracle, teacher-forced from the reference's tree over 8 consecutive frames:
+      * topology, coordinates and new nodes: identical, node for node;
+      * weights of nodes hit by at most one point per pass: identical;
+      * weights of nodes hit by several points in a pass: the reference's plain load/store RACES there
+        (kernel.cu:1361) -- its value must be one of the race's legal outcomes (between one and all of the
+        colliding updates applied), and the engine's must be the defined one: once per node per pass."""
     import gpu_icp_slam_b200 as g
     tree, robot = _grown_tree(scans, n_frames)
     t3kd.t3_set_alloc_fill(0xFF)                               # Q10: the tail of dev_free is NaN points
     t3kd.t3_kd_set(tree.ctypes.data, len(tree))
-    cur = tree
+    n_raced = n_collapsed = 0
     with g.ParticleFilter(32, path=g.PATH_KD) as pf:
-        pf.set_kd(tree)
         for k, f in enumerate(range(n_frames + 1, n_frames + 9)):
+            before = _ref_tree(t3kd)                            # teacher forcing: both start from the reference's tree
+            pf.set_kd(before)
             sc = np.ascontiguousarray(scans[f])
             pose = robot + np.float32(k) * np.array([0.013, -0.008, 0.004], np.float32)
             t3kd.t3_set_robot(*[C.c_float(float(v)) for v in pose])
@@ -363,11 +374,27 @@ def test_kd_map_update_equals_reference(t3kd, scans, n_frames):
             ref_tree = _ref_tree(t3kd)
             pf.update_grid(sc, pose)
             mine = pf.get_kd()
+            want, hf, hw = _oracle_update_map(before, pose, sc, with_hits=True)
+            assert np.array_equal(mine, want), "engine tree != oracle tree at frame %d" % f
             assert len(mine) == len(ref_tree), "frame %d: %d nodes vs reference %d" % (f, len(mine), len(ref_tree))
-            assert np.array_equal(mine, ref_tree), "frame %d: %d nodes differ" % (f, (mine != ref_tree).any(axis=1).sum())
-            cur = _oracle_update_map(cur, pose, sc)
-            assert np.array_equal(cur, ref_tree), "oracle tree differs at frame %d" % f
+            assert np.array_equal(mine[:, :7], ref_tree[:, :7]), "frame %d: topology / coordinates differ" % f
+            nb = len(before)
+            assert np.array_equal(mine[nb:], ref_tree[nb:]), "frame %d: inserted nodes differ" % f
+            w0 = before[:, 7].copy().view(np.float32).astype(np.float64)
+            wm = mine[:nb, 7].copy().view(np.float32).astype(np.float64)
+            wr = ref_tree[:nb, 7].copy().view(np.float32).astype(np.float64)
+            single = (hf[:nb] <= 1) & (hw[:nb] <= 1)
+            assert np.array_equal(wm[single], wr[single]), "frame %d: %d un-raced nodes differ" % (f, (wm[single] != wr[single]).sum())
+            for i in np.flatnonzero(~single):
+                legal = {float(_clamp113(_clamp113(w0[i] - a) + 4.0 * b)) for a in (range(1, hf[i] + 1) if hf[i] else [0])
+                         for b in (range(1, hw[i] + 1) if hw[i] else [0])}
+                assert float(wr[i]) in legal, "frame %d node %d: reference weight %g is not a legal race outcome of %g (%d free, %d wall hits)" % (
+                    f, i, wr[i], w0[i], hf[i], hw[i])
+                assert wm[i] == float(_clamp113(_clamp113(w0[i] - (1 if hf[i] else 0)) + (4.0 if hw[i] else 0.0)))
+                n_raced += 1
+                n_collapsed += int(wm[i] == wr[i])
     t3kd.t3_set_alloc_fill(-1)
+    print("raced nodes: %d, of which the reference collapsed to the once-per-pass value: %d" % (n_raced, n_collapsed))
 
 
 def test_kd_free_running_against_reference_driver(t3kd, scans):
