@@ -39,6 +39,32 @@ inline cudaError_t launch_k(bool dependent, void (*kern)(KArgs...), dim3 grid, d
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// In-graph timeline (pfslam_debug_trace): when on, thread 0 of every block folds %globaltimer into its kernel's
+// [first entry, last exit] pair -- the only way to see where the kernels of the captured step really run (programmatic
+// dependent launches and graph branches overlap them; events cannot be recorded inside a graph replay).
+enum { kTrMotion = 0, kTrTilePrep, kTrScore, kTrScoreFast, kTrCombine, kTrWeights, kTrResample, kTrMapFree, kTrMapWall, kTrPublish, kTrCount };
+__device__ int g_trace_on = 0;
+__device__ unsigned long long g_trace[2 * 16];
+struct TraceScope {
+    int id;
+    __device__ __forceinline__ explicit TraceScope(int i) : id(i)
+    {
+        if (g_trace_on && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMin(&g_trace[2 * id], t);
+        }
+    }
+    __device__ __forceinline__ ~TraceScope()
+    {
+        if (g_trace_on && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMax(&g_trace[2 * id + 1], t);
+        }
+    }
+};
+
 // host side: per-kernel lap events of the serialised profiling step (pfslam_profile_laps)
 enum { kLapStart = -1, kLapMotion = 0, kLapTilePrep, kLapScoreTiled, kLapScoreFast, kLapCombine, kLapWeights,
        kLapPrefix, kLapMapFree, kLapMapWall, kLapResample, kLapCount };
@@ -109,6 +135,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
          float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row,
          const float *__restrict__ scan_src, float *__restrict__ scan_dst, int n_beams)
 {
+    TraceScope trace_scope(kTrMotion);
     __shared__ int s_b[6];
     pdl_trigger();                              // k_tile_prep's blocks may be staged now; they wait for this grid
     // host API step (pfslam_step): the frame's scan is pulled from the pinned, device-mapped staging buffer by the
@@ -155,6 +182,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
 // host API step: the frame result goes to the pinned, device-mapped result record from the last node of the graph
 __global__ void k_publish_result(const FrameResult *__restrict__ res, FrameResult *__restrict__ host_res)
 {
+    TraceScope trace_scope(kTrPublish);
     const int *s = reinterpret_cast<const int *>(res);
     int *d = reinterpret_cast<int *>(host_res);
     for (int i = threadIdx.x; i < (int)(sizeof(FrameResult) / 4); i += blockDim.x) d[i] = s[i];
@@ -349,6 +377,7 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
                float *tiles_local, int fuse_prefix, int n_global, float *__restrict__ prefix,
                FrameResult *__restrict__ res, int write_pose, int *__restrict__ done_counter)
 {
+    TraceScope trace_scope(kTrWeights);
     __shared__ float s_wtot[8], s_wmax[8];
     __shared__ int s_last;
     pdl_trigger();                              // k_resample's blocks may be staged
@@ -523,6 +552,7 @@ k_resample(const Xchg xc, FrameResult *res, const float *__restrict__ prefix,
            const StepParams *__restrict__ sp, float *__restrict__ x, float *__restrict__ y,
            float *__restrict__ th, float *__restrict__ w)
 {
+    TraceScope trace_scope(kTrResample);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();                                 // k_weights_scan's prefix, decision and tiles
     if (i >= n_local || !res->resampled) return;
@@ -622,6 +652,7 @@ k_map_free(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle,
            unsigned *__restrict__ free_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
+    TraceScope trace_scope(kTrMapFree);
     __shared__ int s_cnt;
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
@@ -676,6 +707,7 @@ k_map_wall(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
            unsigned *__restrict__ wall_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
+    TraceScope trace_scope(kTrMapWall);
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;

@@ -99,6 +99,7 @@ k_score_fast(const int8_t *__restrict__ grid, MapGeom g, const float *__restrict
              const ScoreFilteredWork *__restrict__ wk, int *__restrict__ partial,
              int *__restrict__ counters)
 {
+    TraceScope trace_scope(kTrScoreFast);
     const float *__restrict__ scan = sp->scan;
     if (blockIdx.y == kFastSlices) {
         // extra block row: the slow beams (r >= 20 m, sentinel, NaN), exact for every particle; usually 0-3

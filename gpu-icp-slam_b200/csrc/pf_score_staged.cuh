@@ -27,7 +27,6 @@
 namespace pf {
 
 constexpr int kStageWindows = 4;            // windows resident per stage
-constexpr int kStagedQueueCap = 2048;       // (particle, window) records with at least one uncertain beam, per block
 
 // A window's buffer holds the gather layout (128 rows of pitch 272) in its first kSkewBytes.  The TMA box lands
 // DENSE in the tail of the same buffer, at kLandOffset: re-laying row r out writes bytes [272 r, 272 r + 137),
@@ -39,15 +38,19 @@ constexpr int kWinBufBytes = 34944;                   // 273 * 128 >= kLandOffse
 static_assert(kLandOffset + kTileBytes <= kWinBufBytes && kSkewBytes <= kWinBufBytes, "window buffer");
 static_assert(127 * kSkewPitch + 137 <= kLandOffset + 127 * kTileX, "in-place re-layout");
 
-template <int K>
+constexpr int kWarpQueueCap = 96;           // uncertain (particle, window) records per warp between two drains
+
+template <int K, int NWARPS>
 struct StagedSmem {
     alignas(128) int8_t buf[K][kWinBufBytes];         // the stage's windows
     alignas(16) float4 cst[K][kChunkBeams];           // beam constants of the stage's windows
-    uint2 queue[kStagedQueueCap];                     // {particle << 8 | window slot, mask of uncertain beams}
+    float2 bm[K][kChunkBeams];                        // {angle, range} of the same beams, for the exact re-evaluations
+    uint2 queue[NWARPS][kWarpQueueCap];               // per warp: {particle << 2 | window of the stage, mask of uncertain beams}
     alignas(16) int4 win[kMaxChunks];                 // {x0, y0, beam count, window slot} of order[i]
     int bcum[kMaxChunks + 1];                         // beams before window i (pure counts)
+    unsigned long long wbase[K];                      // shared-memory address of buf[k], in the high word (IMAD.WIDE addend)
     alignas(8) uint64_t bar;
-    int qn, npairs;
+    int npairs;
 };
 
 // half a dense row (64 bytes) of a landed box -> registers; then registers -> the pitch-272 gather layout
@@ -72,11 +75,20 @@ __device__ __forceinline__ void relayout_store(int8_t *__restrict__ buf, int tas
 // timing experiments only (PFSLAM_STAGED_DEBUG, results are then WRONG): 1 = skip the exact drain, 2 = skip the TMA loads
 // and the re-layout, 4 = skip the gather loops, 8 = skip the per-window mask / queue code
 __device__ int g_staged_dbg = 0;
+// dbg & 16: thread 0 of every block stamps %globaltimer at its phase boundaries: [block][0] entry, [1] after the
+// dependency wait, [2] prologue done, [3] sum of stage loads, [4] sum of piece set-ups (loads, sincos), [5] sum of gather
+// + queue code, [6] sum of REDs, [7] drain, [8] exit, [9] pieces, [10] stages  (nanoseconds)
+__device__ unsigned long long g_staged_ts[256 * 12];
+__device__ __forceinline__ unsigned long long staged_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
-// VAR selects the address / mask instructions of the gather loop (measured on the B200 with tools/probes/pipe_probe.cu:
-// IMAD.HI issues at half the rate of IMAD / IMAD.WIDE / PRMT / LOP3 / LEA; IADD is accepted by both math pipes):
-//   0: mad.hi.u32 + predicated OR        1: mad.wide.u32 (high word) + predicated ADD for the mask
-//   2: LEA.HI-style shift-add + base add + predicated ADD
+// VAR selects the address instructions of the gather loop (measured on the B200 with tools/probes/pipe_probe.cu:
+// IMAD.HI issues at half the rate of IMAD / IMAD.WIDE / PRMT / LOP3 / LEA; the loop is issue-bound, so instructions
+// are what counts):   1: PRMT + one IMAD.WIDE whose 64-bit addend carries the window base     2: PRMT + IADD + LEA.HI
 template <int THREADS, int PPT, int K, int VAR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
@@ -84,14 +96,20 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
                const StepParams *__restrict__ sp, const float *__restrict__ angle,
                const TiledWork *__restrict__ tw, int *__restrict__ acc_row, int *__restrict__ counters)
 {
+    TraceScope trace_scope(kTrScore);
     constexpr int GP = THREADS * PPT;           // particles per group
+    constexpr int NWARPS = THREADS / 32;
     const float *__restrict__ scan = sp->scan;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    StagedSmem<K> &sm = *reinterpret_cast<StagedSmem<K> *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+    StagedSmem<K, NWARPS> &sm = *reinterpret_cast<StagedSmem<K, NWARPS> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long ts_entry = staged_now();
     pdl_wait();                                 // k_tile_prep's window table
     const int n_chunks = tw->n_chunks;
     const int dbg = g_staged_dbg;
+    const bool stamp = (dbg & 16) && tid == 0 && blockIdx.x < 256;
+    unsigned long long ts_wait = staged_now(), ts_acc[4] = {0, 0, 0, 0}, ts_last = 0;
+    int n_pieces = 0, n_stage_loads = 0;
 
     for (int i = tid; i < n_chunks; i += THREADS) {
         const int sl = tw->order[i];
@@ -101,8 +119,9 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
     if (tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sm.qn = 0; sm.npairs = 0;
+        sm.npairs = 0;
     }
+    if (tid < K) sm.wbase[tid] = (unsigned long long)smem_u32(sm.buf[tid]) << 32;
     __syncthreads();
     if (tid < 32) {                             // beams before each window
         int run = 0;
@@ -119,6 +138,8 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
     }
     __syncthreads();
     const int b_total = sm.bcum[n_chunks];
+    const unsigned long long ts_prologue = staged_now();
+    ts_last = ts_prologue;
     if (b_total <= 0) return;
     const int n_groups = (n + GP - 1) / GP;
     const long long total = (long long)n_groups * b_total;
@@ -132,8 +153,29 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
     const float irx = (float)(1.0 / (double)g.res_x), iry = (float)(1.0 / (double)g.res_y);
     const float mconst = kMagicT + 0.5f * unit + kGuardT;      // exact
     uint32_t ph = 0;                            // phase of the stage barrier
-    int n_inline = 0;                           // pairs this thread re-evaluated inline (queue overflow)
+    int n_exact = 0;                            // pairs this thread re-evaluated with the exact expression
+    int qcnt = 0;                               // records in this warp's queue (warp-uniform)
     int s = 0;
+
+    // the warp's queued uncertain pairs, re-evaluated with the reference's exact expression (beam data of the
+    // CURRENT stage from shared memory: called before the stage changes, and at the end)
+    auto drain = [&]() {
+        if (dbg & 1) { qcnt = 0; return; }
+        for (int qi = lane; qi < qcnt; qi += 32) {
+            const uint2 e = sm.queue[warp][qi];
+            const int p = (int)(e.x >> 2), kw = (int)(e.x & 3u);
+            const float qx = x[p], qy = y[p], qt = th[p];
+            int v = 0;
+            n_exact += __popc(e.y);
+            for (unsigned m = e.y; m; m &= m - 1) {
+                const float2 ar = sm.bm[kw][__ffs(m) - 1];
+                v += eval_exact(grid, g, c0x, c0y, qx, qy, qt, ar.x, ar.y);
+            }
+            if (v) atomicAdd(&acc_row[p], v);
+        }
+        __syncwarp();
+        qcnt = 0;
+    };
 
     long long u = lo;
     int staged = -1;
@@ -142,40 +184,44 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
         const int w0 = K * s, w1 = min(w0 + K, n_chunks);
         if (s != staged) {
             // ---- stage the windows of stage s: all boxes in flight at once, the beam constants meanwhile
+            if (staged >= 0) drain();           // while the previous stage's beam table is still there
             __syncthreads();                    // every warp has left the previous stage's gather loops
-            if (!(dbg & 2)) {
-            if (tid == 0) {
+            if (tid == 0 && !(dbg & 2)) {
                 mbar_expect_tx(&sm.bar, (uint32_t)(w1 - w0) * kTileBytes);
                 for (int k = w0; k < w1; k++) {
                     const int4 wi = sm.win[k];
                     tma_load_2d(sm.buf[k - w0] + kLandOffset, &tmap, wi.y, wi.x, &sm.bar);
                 }
             }
-            }
             for (int i = tid; i < (w1 - w0) * kChunkBeams; i += THREADS) {
                 const int k = i / kChunkBeams, b = i - k * kChunkBeams;
                 const int4 wi = sm.win[w0 + k];
-                sm.cst[k][b] = b < wi.z ? tw->tconst[wi.w * kChunkBeams + b] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                float2 ar = make_float2(0.f, 0.f);
+                if (b < wi.z) {
+                    c = tw->tconst[wi.w * kChunkBeams + b];
+                    const int j = tw->tbeam[wi.w * kChunkBeams + b];
+                    ar = make_float2(angle[j], scan[j]);
+                }
+                sm.cst[k][b] = c; sm.bm[k][b] = ar;
             }
             if (!(dbg & 2)) {
-            mbar_wait(&sm.bar, ph); ph ^= 1u;
-            // in-place re-layout, 256 half-row tasks per window: all dense rows into registers, barrier, then out
-            constexpr int kRounds = (K * 256 + THREADS - 1) / THREADS;
-            uint32_t w[kRounds][17];
-#pragma unroll
-            for (int r = 0; r < kRounds; r++) {
-                const int t = tid + r * THREADS;
-                if (t < (w1 - w0) * 256) relayout_load(sm.buf[t >> 8], t & 255, w[r]);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < kRounds; r++) {
-                const int t = tid + r * THREADS;
-                if (t < (w1 - w0) * 256) relayout_store(sm.buf[t >> 8], t & 255, w[r]);
-            }
+                mbar_wait(&sm.bar, ph); ph ^= 1u;
+                // in-place re-layout, 256 half-row tasks per window; per round of THREADS tasks: dense half rows into
+                // registers, barrier, then out (a round never shares a window with the next one's loads: THREADS % 256 == 0)
+                static_assert(THREADS % 256 == 0, "re-layout rounds must cover whole windows");
+#pragma unroll 1
+                for (int t = tid; t < ((K * 256 + THREADS - 1) / THREADS) * THREADS; t += THREADS) {   // same trip count for every thread
+                    const bool mine = t < (w1 - w0) * 256;
+                    uint32_t w[17];
+                    if (mine) relayout_load(sm.buf[t >> 8], t & 255, w);
+                    __syncthreads();
+                    if (mine) relayout_store(sm.buf[t >> 8], t & 255, w);
+                }
             }
             __syncthreads();                    // skewed windows and constants visible
             staged = s;
+            if (stamp) { const unsigned long long t = staged_now(); ts_acc[0] += t - ts_last; ts_last = t; n_stage_loads++; }
         }
         const int bc = sm.bcum[w0], bs = sm.bcum[w1] - bc;
         const long long up = u - (long long)n_groups * bc;
@@ -198,13 +244,15 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
             sincosf(th[pc], &sn[k], &cs[k]);
             acc[k] = 0;
         }
+        if (stamp) { const unsigned long long t = staged_now(); ts_acc[1] += t - ts_last; ts_last = t; n_pieces++; }
         for (int wi_ = w0; wi_ < w1; wi_++) {
             const int4 wi = sm.win[wi_];
             const int cb0 = sm.bcum[wi_] - bc;
             const int lb0 = max(b0 - cb0, 0), lb1 = min(b1 - cb0, wi.z);
             if (lb0 >= lb1) continue;
             const int kw = wi_ - w0;
-            const uint32_t base = smem_u32(sm.buf[kw]);
+            const unsigned long long base64 = sm.wbase[kw];     // from shared memory on purpose: a vector register pair
+            const uint32_t base = (uint32_t)(base64 >> 32);
             const float offx = __fsub_rn(c0x, (float)wi.x), offy = __fsub_rn(c0y, (float)wi.y);
             float2 P[PPT];
             unsigned um[PPT];
@@ -215,8 +263,9 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
                 um[k] = 0u;
             }
             unsigned bit = 1u << lb0;
-            // Gather loop, per evaluation: 2 FFMA2, PRMT, IMAD.HI (address), LDS.S8, 2 LOP3 (guard band), then the add
-            // (certain) or the beam's bit in the particle's mask (uncertain).
+            // Gather loop, per evaluation: 2 FFMA2, PRMT, IMAD.WIDE (address), LDS.S8, 2 LOP3 (guard band), then the add
+            // (certain) or the beam's bit in the particle's mask (uncertain; a bit is set at most once, so ADD == OR
+            // and the instruction can go to either math pipe).
 #pragma unroll 4
             for (int b = (dbg & 4) ? lb1 : lb0; b < lb1; b++) {
                 const float4 q = sm.cst[kw][b];
@@ -226,14 +275,11 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
                     const float2 t2 = __ffma2_rn(qhi, make_float2(cs[k], cs[k]), __ffma2_rn(qlo, make_float2(sn[k], sn[k]), P[k]));
                     const uint32_t bx = __float_as_uint(t2.x), by = __float_as_uint(t2.y);
                     uint32_t addr;
-                    if (VAR == 0) {
+                    if (VAR == 1) {
                         const uint32_t idx = prmt(bx, by, 0x26BBu);          // x << 24 | y << 16
-                        addr = __umulhi(idx, 0x11000u) + base;               // (x*256 + y) * 17 / 16 = x*272 + y + (y >> 4)
-                    } else if (VAR == 1) {
-                        const uint32_t idx = prmt(bx, by, 0x26BBu);
-                        unsigned long long wide;
-                        asm("mul.wide.u32 %0, %1, 0x11000;" : "=l"(wide) : "r"(idx));
-                        addr = (uint32_t)(wide >> 32) + base;
+                        unsigned long long wide;                             // high word: base + (x*256 + y) * 17 / 16
+                        asm("mad.wide.u32 %0, %1, 0x11000, %2;" : "=l"(wide) : "r"(idx), "l"(base64));
+                        addr = (uint32_t)(wide >> 32);                       //          = base + x*272 + y + (y >> 4)
                     } else {
                         const uint32_t idx = prmt(bx, by, 0xBB26u);          // x * 256 + y
                         addr = idx + (idx >> 4) + base;
@@ -241,81 +287,48 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
                     int v;
                     asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr));
                     // guard band: bits 7..15 == 0 on either axis -> uncertain (the beam's bit), else add the cell
-                    if (VAR == 0)
-                        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                            "and.b32 t, %2, 0xFF80;\n\t"
-                            "setp.ne.u32 p, t, 0;\n\t"
-                            "lop3.and.b32 t|p, %3, 0xFF80, 0, 0xC0, p;\n\t"   // LOP3.LUT.PAND: p &= (by & mask) != 0
-                            "@!p or.b32 %0, %0, %4;\n\t"
-                            "@p add.s32 %1, %1, %5;\n\t}"
-                            : "+r"(um[k]), "+r"(acc[k]) : "r"(bx), "r"(by), "r"(bit), "r"(v));
-                    else                                                     // a beam's bit is set at most once: ADD == OR
-                        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                            "and.b32 t, %2, 0xFF80;\n\t"
-                            "setp.ne.u32 p, t, 0;\n\t"
-                            "lop3.and.b32 t|p, %3, 0xFF80, 0, 0xC0, p;\n\t"
-                            "@!p add.u32 %0, %0, %4;\n\t"
-                            "@p add.s32 %1, %1, %5;\n\t}"
-                            : "+r"(um[k]), "+r"(acc[k]) : "r"(bx), "r"(by), "r"(bit), "r"(v));
+                    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                        "and.b32 t, %2, 0xFF80;\n\t"
+                        "setp.ne.u32 p, t, 0;\n\t"
+                        "lop3.and.b32 t|p, %3, 0xFF80, 0, 0xC0, p;\n\t"   // LOP3.LUT.PAND: p &= (by & mask) != 0
+                        "@!p add.u32 %0, %0, %4;\n\t"
+                        "@p add.s32 %1, %1, %5;\n\t}"
+                        : "+r"(um[k]), "+r"(acc[k]) : "r"(bx), "r"(by), "r"(bit), "r"(v));
                 }
                 bit <<= 1;
             }
-            // uncertain pairs (not added above): one record per (particle, window); one shared-memory atomic per warp
-            {
-                unsigned mk[PPT];
-                int cntm = 0;
+            // uncertain pairs (not added above): one record per (particle, window) in the warp's own queue
+            if (!(dbg & 8)) {
 #pragma unroll
-                for (int k = 0; k < PPT; k++) { mk[k] = valid[k] ? um[k] : 0u; cntm += mk[k] ? 1 : 0; }
-                if (!(dbg & 8) && __any_sync(0xffffffffu, cntm)) {
-                    int inc = cntm;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                    int qb = 0;
-                    if (lane == 31) qb = atomicAdd(&sm.qn, inc);
-                    qb = __shfl_sync(0xffffffffu, qb, 31);
-                    int qi = qb + inc - cntm;
-#pragma unroll
-                    for (int k = 0; k < PPT; k++) {
-                        if (!mk[k]) continue;
-                        const int p = gq * GP + tid + k * THREADS;
-                        if (qi < kStagedQueueCap) sm.queue[qi] = make_uint2(((unsigned)p << 8) | (unsigned)wi.w, mk[k]);
-                        else {
-                            const float qt = th[p];
-                            n_inline += __popc(mk[k]);
-                            for (unsigned m = mk[k]; m; m &= m - 1) {
-                                const int j = tw->tbeam[wi.w * kChunkBeams + __ffs(m) - 1];
-                                acc[k] += eval_exact(grid, g, c0x, c0y, px[k], py[k], qt, angle[j], scan[j]);
-                            }
-                        }
-                        qi++;
-                    }
+                for (int k = 0; k < PPT; k++) {
+                    const unsigned mk = valid[k] ? um[k] : 0u;
+                    const unsigned hot = __ballot_sync(0xffffffffu, mk != 0u);
+                    if (!hot) continue;
+                    if (qcnt + __popc(hot) > kWarpQueueCap) drain();
+                    if (mk) sm.queue[warp][qcnt + __popc(hot & ((1u << lane) - 1u))] = make_uint2(((unsigned)(gq * GP + tid + k * THREADS) << 2) | (unsigned)kw, mk);
+                    qcnt += __popc(hot);
                 }
+                __syncwarp();
             }
         }
+        if (stamp) { const unsigned long long t = staged_now(); ts_acc[2] += t - ts_last; ts_last = t; }
 #pragma unroll
         for (int k = 0; k < PPT; k++)
             if (valid[k] && acc[k]) atomicAdd(&acc_row[gq * GP + tid + k * THREADS], acc[k]);
+        if (stamp) { const unsigned long long t = staged_now(); ts_acc[3] += t - ts_last; ts_last = t; }
     }
 
-    // ---- drain: the uncertain pairs of the whole slice, re-evaluated with the reference's exact expression
-    __syncthreads();
-    const int qn = (dbg & 1) ? 0 : min(sm.qn, kStagedQueueCap);
-    int np = n_inline;
-    for (int qi = tid; qi < qn; qi += THREADS) {
-        const uint2 e = sm.queue[qi];
-        const int p = (int)(e.x >> 8), c = (int)(e.x & 0xffu);
-        const float qx = x[p], qy = y[p], qt = th[p];
-        int v = 0;
-        np += __popc(e.y);
-        for (unsigned m = e.y; m; m &= m - 1) {
-            const int j = tw->tbeam[c * kChunkBeams + __ffs(m) - 1];
-            v += eval_exact(grid, g, c0x, c0y, qx, qy, qt, angle[j], scan[j]);
-        }
-        if (v) atomicAdd(&acc_row[p], v);
-    }
-    if (np) atomicAdd(&sm.npairs, np);
+    // ---- the rest of the warp's uncertain pairs
+    drain();
+    if (n_exact) atomicAdd(&sm.npairs, n_exact);
     __syncthreads();
     if (tid == 0 && sm.npairs) atomicAdd(&counters[2], sm.npairs);
+    if (stamp) {
+        unsigned long long *o = g_staged_ts + blockIdx.x * 12;
+        const unsigned long long t = staged_now();
+        o[0] = ts_entry; o[1] = ts_wait; o[2] = ts_prologue; o[3] = ts_acc[0]; o[4] = ts_acc[1]; o[5] = ts_acc[2]; o[6] = ts_acc[3];
+        o[7] = t - ts_last; o[8] = t; o[9] = (unsigned long long)n_pieces; o[10] = (unsigned long long)n_stage_loads;
+    }
 }
 
 // block shape: 768 threads x 4 particles (default) or 1024 x 2 (PFSLAM_STAGED_THREADS=1024); gather-loop variant
@@ -329,24 +342,26 @@ static int staged_threads()
 static int staged_variant()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("PFSLAM_STAGED_VARIANT"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+    if (v < 0) { const char *e = getenv("PFSLAM_STAGED_VARIANT"); v = e ? atoi(e) : 2; if (v != 1) v = 2; }
     return v;
 }
 
 static StagedKernel staged_kernel()
 {
     const int t = staged_threads(), v = staged_variant();
-    if (t == 1024) return v == 0 ? (StagedKernel)k_score_staged<1024, 2, kStageWindows, 0> : v == 1 ? (StagedKernel)k_score_staged<1024, 2, kStageWindows, 1>
-                                                                                             : (StagedKernel)k_score_staged<1024, 2, kStageWindows, 2>;
-    return v == 0 ? (StagedKernel)k_score_staged<768, 4, kStageWindows, 0> : v == 1 ? (StagedKernel)k_score_staged<768, 4, kStageWindows, 1>
-                                                                            : (StagedKernel)k_score_staged<768, 4, kStageWindows, 2>;
+    if (t == 1024) return v == 1 ? (StagedKernel)k_score_staged<1024, 2, kStageWindows, 1> : (StagedKernel)k_score_staged<1024, 2, kStageWindows, 2>;
+    return v == 1 ? (StagedKernel)k_score_staged<768, 4, kStageWindows, 1> : (StagedKernel)k_score_staged<768, 4, kStageWindows, 2>;
+}
+static size_t staged_smem_bytes()
+{
+    return staged_threads() == 1024 ? sizeof(StagedSmem<kStageWindows, 32>) : sizeof(StagedSmem<kStageWindows, 24>);
 }
 
 // returns the grid size of k_score_staged = SMs x resident blocks per SM (one full wave), or -1
 static int score_staged_setup(int device)
 {
     int per_sm = 0, n_sm = 0;
-    const size_t smem = sizeof(StagedSmem<kStageWindows>);
+    const size_t smem = staged_smem_bytes();
     if (cudaFuncSetAttribute(staged_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, staged_kernel(), staged_threads(), smem) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;

@@ -134,6 +134,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             const double2 *__restrict__ angle_cs, int n_beams, MapGeom g,
             ScoreFilteredWork *__restrict__ wk, TiledWork *tw)
 {
+    TraceScope trace_scope(kTrTilePrep);
     pdl_trigger();                              // k_score_tiled's blocks may be staged
     pdl_wait();                                 // k_motion's cloud bounds
     const float *__restrict__ scan = sp->scan;
@@ -603,6 +604,7 @@ k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gid
                      const float *__restrict__ y, const float *__restrict__ th, Extrema *__restrict__ ext_out,
                      int *__restrict__ done_counter, const Xchg xc, const StepParams *__restrict__ sp)
 {
+    TraceScope trace_scope(kTrCombine);
     __shared__ int smin[8];
     __shared__ long long smax[8];
     __shared__ int s_last;

@@ -628,7 +628,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
                                     e->cfg.n_beams, e->fit, e->blk_min, e->blk_maxkey, e->ext_local, e->fwork,
                                     e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->tiled_grid, e->stream, ev0, ev1,
                                     use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr,
-                                    e->staged ? staged_kernel() : nullptr, staged_threads(), sizeof(StagedSmem<kStageWindows>),
+                                    e->staged ? staged_kernel() : nullptr, staged_threads(), staged_smem_bytes(),
                                     staged_threads() * (staged_threads() == 1024 ? 2 : 4));
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
@@ -1368,6 +1368,33 @@ int pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes)
 }
 
 int64_t pfslam_launch_count(pfslam_engine *e) { return e ? e->launches : 0; }
+
+static const char *const kTraceNames[kTrCount] = {"k_motion", "k_tile_prep", "k_score_staged", "k_score_fast", "k_score_combine_rows",
+                                                  "k_weights_scan", "k_resample", "k_map_free", "k_map_wall", "k_publish_result"};
+const char *pfslam_trace_name(int32_t id) { return id >= 0 && id < kTrCount ? kTraceNames[id] : ""; }
+
+// on != 0: switch the in-kernel timeline on and reset it; out (optional, 2 * PFSLAM_TRACE_COUNT words): the [first
+// entry, last exit] %globaltimer pairs recorded since the last reset.  The caller synchronises around it.
+int pfslam_debug_trace(int32_t on, uint64_t *out)
+{
+    unsigned long long tab[2 * 16];
+    if (out) {
+        CUDA_TRY(cudaMemcpyFromSymbol(tab, g_trace, sizeof tab));
+        memcpy(out, tab, sizeof(uint64_t) * 2 * kTrCount);
+    }
+    for (int i = 0; i < 16; i++) { tab[2 * i] = ~0ull; tab[2 * i + 1] = 0ull; }
+    CUDA_TRY(cudaMemcpyToSymbol(g_trace, tab, sizeof tab));
+    const int v = on ? 1 : 0;
+    CUDA_TRY(cudaMemcpyToSymbol(g_trace_on, &v, sizeof v));
+    return PFSLAM_OK;
+}
+
+int pfslam_debug_staged_timing(uint64_t *out, int32_t n_words)
+{
+    if (!out || n_words <= 0 || n_words > 256 * 12) return set_error(PFSLAM_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaMemcpyFromSymbol(out, g_staged_ts, sizeof(uint64_t) * (size_t)n_words));
+    return PFSLAM_OK;
+}
 
 int pfslam_debug_trig(int32_t device, const float *x_host, int64_t n, float *cos_out, float *sin_out)
 {

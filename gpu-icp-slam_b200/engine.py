@@ -112,6 +112,9 @@ _SIGS = {
     "pfslam_profile_laps_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pfslam_lap_name": (C.c_char_p, [C.c_int32]),
     "pfslam_debug_trig": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pfslam_debug_staged_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pfslam_debug_trace": (C.c_int, [C.c_int32, C.c_void_p]),
+    "pfslam_trace_name": (C.c_char_p, [C.c_int32]),
 }
 
 
@@ -144,6 +147,23 @@ def debug_trig(x, device=0):
     if rc != 0:
         raise PfslamError("pfslam error %d: %s" % (rc, lib.pfslam_last_error().decode()))
     return c, s
+
+
+TRACE_COUNT = 10
+
+
+def debug_trace(on=True, read=False):
+    """in-graph timeline of the 2D step's kernels: {kernel: (first entry, last exit)} in ns of %globaltimer for the
+    launches since the last call (None when read is False); resets the table and switches tracing on / off"""
+    lib = load_library()
+    buf = np.zeros(2 * TRACE_COUNT, np.uint64)
+    rc = lib.pfslam_debug_trace(1 if on else 0, buf.ctypes.data if read else None)
+    if rc != 0:
+        raise PfslamError("pfslam error %d: %s" % (rc, lib.pfslam_last_error().decode()))
+    if not read:
+        return None
+    return {lib.pfslam_trace_name(i).decode(): (int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(TRACE_COUNT)
+            if buf[2 * i + 1] > 0}
 
 
 def exported_symbols():

@@ -198,6 +198,17 @@ int  pfslam_profile_laps(pfslam_engine *e, int32_t on);
 int  pfslam_profile_laps_read(pfslam_engine *e, float ms_mean[PFSLAM_LAP_COUNT], int32_t count[PFSLAM_LAP_COUNT]);
 const char *pfslam_lap_name(int32_t id);
 
+/* tuning hook: in-graph timeline.  While on, every kernel of the 2D step folds %globaltimer into a [first entry, last
+ * exit] pair; (on, out): copy the pairs recorded so far (2 * PFSLAM_TRACE_COUNT words, nanoseconds), then reset.
+ * The caller synchronises the engine's stream around the call. */
+#define PFSLAM_TRACE_COUNT 10
+int  pfslam_debug_trace(int32_t on, uint64_t *out);
+const char *pfslam_trace_name(int32_t id);
+
+/* tuning hook: with PFSLAM_STAGED_DEBUG & 16 the scoring kernel's blocks stamp their phase boundaries
+ * (12 words per block, see pf_score_staged.cuh); copies the first n_words of that table */
+int  pfslam_debug_staged_timing(uint64_t *out, int32_t n_words);
+
 /* test hook: libdevice cosf/sinf of n host floats evaluated on the device (the functions the
  * reference's kernels call, kernel.cu:185-186); test hook: lets the test suite validate its CPU emulation of them */
 int  pfslam_debug_trig(int32_t device, const float *x_host, int64_t n, float *cos_out, float *sin_out);

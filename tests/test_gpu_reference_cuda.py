@@ -400,27 +400,40 @@ def test_kd_map_update_equals_reference(t3kd, scans, n_frames):
 def test_kd_free_running_against_reference_driver(t3kd, scans):
     """the reference's particleFilter() itself (kernel.cu:1702-1768: the kd step at HEAD, including the
     frame%100==5 rebalance) against the engine's kd step, both free-running from an empty map at the
-    reference's PARTICLE_COUNT.  Not bit comparable (thrust scan / reduce order, racy in-place resample,
-    approximate SVD); trajectories and trees must agree closely.  Up to three attempts (the reference run
-    is not repeatable)."""
+    reference's PARTICLE_COUNT.  Not bit comparable: thrust scan / reduce order, the racy in-place resample
+    (kernel.cu:441), the racy weight update (kernel.cu:1361) and the approximate SVD make the reference's own
+    runs differ from each other.  The yardstick is therefore the reference against itself: three reference
+    runs give the run-to-run spread of trajectory and tree size; the engine's run must lie within 1.5x that
+    spread (+2 cm) of the nearest reference run."""
     import gpu_icp_slam_b200 as g
-    seen = []
+    frames = 120
+    ref_traj, ref_size = [], []
     for _ in range(3):
         assert t3kd.t3_init(SCENE.encode()) == 0
         t3kd.t3_reset_kd()
         t3kd.t3_set_alloc_fill_sized(0xFF, ICP_BUF_BYTES, 0)
-        d, sizes = [], None
-        with g.ParticleFilter(N, path=g.PATH_KD) as pf:
-            for f in range(1, 121):
-                sc = np.ascontiguousarray(scans[f])
-                t3kd.t3_particle_filter(P(sc), f)
-                r = pf.step(sc, f)
-                pose = np.zeros(3, np.float32)
-                t3kd.t3_get_robot(P(pose))
-                d.append(float(np.hypot(r.pose[0] - pose[0], r.pose[1] - pose[1])))
-            sizes = (r.kd_size, t3kd.t3_kd_size())
+        tr = np.zeros((frames, 3), np.float32)
+        for f in range(1, frames + 1):
+            sc = np.ascontiguousarray(scans[f])
+            t3kd.t3_particle_filter(P(sc), f)
+            t3kd.t3_get_robot(P(tr[f - 1]))
+        ref_traj.append(tr)
+        ref_size.append(t3kd.t3_kd_size())
         t3kd.t3_set_alloc_fill(-1)
-        seen.append((round(max(d), 4), sizes))
-        if np.isfinite(max(d)) and max(d) < 0.10 and abs(sizes[0] - sizes[1]) < 0.1 * sizes[1]:
-            return
-    raise AssertionError("no attempt agreed with the reference kd driver: %s" % (seen,))
+    mine = np.zeros((frames, 3), np.float32)
+    with g.ParticleFilter(N, path=g.PATH_KD) as pf:
+        for f in range(1, frames + 1):
+            r = pf.step(np.ascontiguousarray(scans[f]), f)
+            mine[f - 1] = list(r.pose)
+        my_size = r.kd_size
+
+    def dist(a, b):
+        return float(np.hypot(a[:, 0] - b[:, 0], a[:, 1] - b[:, 1]).max())
+    spread = max(dist(ref_traj[i], ref_traj[j]) for i in range(3) for j in range(i + 1, 3))
+    mine_d = min(dist(mine, t) for t in ref_traj)
+    size_lo, size_hi = min(ref_size), max(ref_size)
+    msg = "engine-to-nearest-reference %.4f m, reference run-to-run %.4f m; sizes %d vs reference %r" % (mine_d, spread, my_size, ref_size)
+    print(msg)
+    assert np.isfinite(mine).all() and all(np.isfinite(t).all() for t in ref_traj), msg
+    assert mine_d <= 1.5 * spread + 0.02, msg
+    assert size_lo - 0.15 * size_hi <= my_size <= size_hi + 0.15 * size_hi, msg

@@ -17,11 +17,28 @@ sc = S.load(p)[1500:] if os.path.exists(p) else S.load(os.path.join(root, "tests
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 with g.ParticleFilter(n) as pf:
-    for f in range(1, frames + 1):
-        pf.step(sc[f], f)
-    pf.phase_motion(frames + 1)
-    pf.upload_scan(sc[frames + 1])
-    t = np.array([pf.profile_score() for _ in range(20)])
+    import time
+    t0 = time.time()
+    f = 0
+    while f < frames or time.time() - t0 < 2.5:        # keep the GPU busy long enough for its clocks to reach the maximum
+        f += 1
+        pf.step(sc[1 + (f - 1) % frames], f)
+    pf.phase_motion(f + 1)
+    pf.upload_scan(sc[1 + f % frames])
+    t = np.array([pf.profile_score() for _ in range(60)])
     print("dbg=%s var=%s thr=%s: kernel mean %.2f us, min %.2f us; phase mean %.2f us" % (
         os.environ.get("PFSLAM_STAGED_DEBUG", "0"), os.environ.get("PFSLAM_STAGED_VARIANT", "-"), os.environ.get("PFSLAM_STAGED_THREADS", "-"),
-        t[5:, 0].mean() * 1e3, t[:, 0].min() * 1e3, t[5:, 1].mean() * 1e3))
+        t[20:, 0].mean() * 1e3, t[:, 0].min() * 1e3, t[20:, 1].mean() * 1e3))
+    if int(os.environ.get("PFSLAM_STAGED_DEBUG", "0")) & 16:
+        from gpu_icp_slam_b200 import engine
+        ts = np.zeros((148, 12), np.uint64)
+        engine.load_library().pfslam_debug_staged_timing(ts.ctypes.data, ts.size)
+        t = ts.astype(np.float64)
+        t0 = t[:, 0].min()
+        names = ["entry(after first block)", "dependency wait", "prologue", "stage loads", "piece set-up", "gather+queue", "REDs", "drain"]
+        vals = [t[:, 0] - t0, t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3], t[:, 4], t[:, 5], t[:, 6], t[:, 7]]
+        for nm, v in zip(names, vals):
+            print("  %-26s mean %7.2f us  max %7.2f us" % (nm, v.mean() / 1e3, v.max() / 1e3))
+        print("  %-26s mean %7.2f us  max %7.2f us; pieces/block %.1f, stage loads/block %.1f" % (
+            "block lifetime", (t[:, 8] - t[:, 0]).mean() / 1e3, (t[:, 8] - t[:, 0]).max() / 1e3, t[:, 9].mean(), t[:, 10].mean()))
+        print("  kernel span (first entry -> last exit) %.2f us" % ((t[:, 8].max() - t0) / 1e3))
