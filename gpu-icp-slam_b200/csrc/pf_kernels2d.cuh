@@ -103,6 +103,7 @@ struct FrameResult {
     int   xchg_timeout;        // sharded engines: a peer-exchange wait ran into its time limit this frame
     int   resample_count;      // steps that resampled so far
     int   wait_ext_ns, wait_tiles_ns;   // accumulated peer-exchange wait times (block 0 / the last block of k_weights_scan)
+    int   n_windows, n_wide;   // tiled scorer: windows placed / beams left to the global-memory path this frame
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
          const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds,
          float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row,
-         const float *__restrict__ scan_src, float *__restrict__ scan_dst, int n_beams)
+         const float *__restrict__ scan_src, float *__restrict__ scan_dst, int n_beams, float4 *__restrict__ pcs)
 {
     TraceScope trace_scope(kTrMotion);
     __shared__ int s_b[6];
@@ -156,6 +157,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
         const float vx = __fadd_rn(x[i], nx), vy = __fadd_rn(y[i], ny), vt = __fadd_rn(th[i], nt);
         x[i] = vx; y[i] = vy; th[i] = vt;
         acc_row[i] = 0;                        // the tiled scorer adds into it (pf_score_tiled.cuh)
+        if (pcs) { float sn, cs; sincosf(vt, &sn, &cs); pcs[i] = make_float4(vx, vy, cs, sn); }   // ... and reads the pose from here
         if (snap) {
             float *sn = snap + (long long)(sp->seq & parity_mask) * snap_stride;
             if (snap_aos) reinterpret_cast<float4 *>(sn)[i] = make_float4(vx, vy, vt, 0.0f);
@@ -732,6 +734,7 @@ k_map_wall(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
         if (atomicAdd(&counters[3], 1) == (int)gridDim.x - 1) {
             res->n_free = atomicAdd(&counters[0], 0); res->n_wall = atomicAdd(&counters[1], 0);
             res->n_slow = atomicAdd(&counters[2], 0);
+            res->n_wide = counters[6]; res->n_windows = counters[7];
             counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
         }
     }

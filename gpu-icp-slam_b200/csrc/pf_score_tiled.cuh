@@ -36,7 +36,8 @@ constexpr int kSkewPitch = 272;             // row pitch of the gather copy (ban
 constexpr int kSkewBytes = kTileX * kSkewPitch + 16;
 constexpr int kChunkBeams = 32;
 constexpr int kMaxGroups = 64;              // groups of 32 consecutive fast beams (2048 beams)
-constexpr int kMaxChunks = 2 * kMaxGroups;  // each group gets up to two windows
+constexpr int kPrepPasses = 4;              // windows a group of 32 beams may get (staging a window is cheap for k_score_staged)
+constexpr int kMaxChunks = kPrepPasses * kMaxGroups;
 constexpr int kTiledGroup = 1024;           // particles per block: 256 threads x 4, or 512 threads x 2 (PFSLAM_TILED_THREADS)
 constexpr int kTiledQueueCap = 1024;        // (particle, window) records with at least one uncertain beam, per group share
 constexpr float kMagicT = 8388608.0f;       // 2^23
@@ -45,6 +46,18 @@ constexpr float kGuardT = 64.0f;            // units of 2^-16 cell; band test = 
 constexpr double kRotBudgetUnits = 26.0;    // share of the rounding of rot = angle + theta in the 64-unit guard band
 constexpr int kBoxMargin = 2;               // cells added around the conservative hit box
 constexpr int kWindowCostBeams = 8;         // fixed cost of a window (TMA wait, re-layout, two barriers) in beam units
+
+// stage table of k_score_staged (pf_score_staged.cuh), built by k_tile_prep's last warp
+constexpr int kStageWindows = 5;            // windows resident per stage (5 x 34.9 KB of shared memory)
+constexpr int kMaxStages = 128;             // tiled stages + wide stages + slow stages of a frame
+enum { kStTiled = 0, kStWide = 1, kStSlow = 2 };
+// Units of the work line, calibrated with the in-kernel stamps (tools/score_probe.py, PFSLAM_STAGED_DEBUG=16): a tiled
+// beam over one particle group = 1 (0.26 us); a wide beam (LDG path) = 4; a slow beam (exact expression) = 6; and every
+// (stage, particle group) piece costs a fixed set-up -- pose loads, per-window offsets, queue pushes, the REDs, mostly
+// latency -- of ~3 us on a tiled stage (5 windows) and ~1.5 us on a wide / slow one.
+constexpr int kWideWeight = 4, kSlowWeight = 6;
+__host__ __device__ constexpr int stage_weight(int kind) { return kind == kStTiled ? 1 : kind == kStWide ? kWideWeight : kSlowWeight; }
+__host__ __device__ constexpr int stage_setup(int kind) { return kind == kStTiled ? 12 : 6; }
 
 struct TileChunk { int x0, y0, count, pad; };
 
@@ -58,6 +71,14 @@ struct TiledWork {
     int bounds[8];                             // cloud bounds as ordered ints: xmin,xmax,ymin,ymax,tmin,tmax
     int wide_run, slow_run;                    // running sizes of the wide / slow lists while k_tile_prep's warps append
     int done;                                  // warps of k_tile_prep that have finished this frame
+    int stat_wide, stat_slow;                  // beam counts of the frame's wide / slow lists (for the frame result)
+    // for k_score_staged: the non-empty windows compacted, their beam prefix, the stage table and the first block of
+    // every stage (stage-aligned slices of the work line)
+    int4 win[kMaxChunks];                      // {x0, y0, beam count, window slot} of order[i]
+    int bcum[kMaxChunks + 1];                  // beams before window i
+    int4 stage[kMaxStages];                    // {kind, first window / list index, beams, units of the line before it (per group)}
+    int sfirst[kMaxStages + 1];                // first block of stage s; sfirst[n_stages] = blocks
+    int n_stages, u_total, aligned;            // aligned: the slices are stage-aligned (enough blocks), else equal cuts
 };
 
 __global__ void k_bounds_reset(TiledWork *__restrict__ tw)
@@ -68,7 +89,7 @@ __global__ void k_bounds_reset(TiledWork *__restrict__ tw)
 // pose bounds of the local particle cloud (min/max of x, y, theta)
 __global__ void __launch_bounds__(256)
 k_cloud_bounds(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
-               TiledWork *__restrict__ tw, int *__restrict__ acc_row)
+               TiledWork *__restrict__ tw, int *__restrict__ acc_row, float4 *__restrict__ pcs)
 {
     __shared__ int s_b[6];
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
@@ -76,7 +97,8 @@ k_cloud_bounds(const float *__restrict__ x, const float *__restrict__ y, const f
     int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int k0 = float_order(x[i]), k1 = float_order(y[i]), k2 = float_order(th[i]);
-        acc_row[i] = 0;                        // k_motion's other job when it did not run this frame
+        acc_row[i] = 0;                        // k_motion's other jobs when it did not run this frame
+        { float sn, cs; sincosf(th[i], &sn, &cs); pcs[i] = make_float4(x[i], y[i], cs, sn); }
         lo[0] = min(lo[0], k0); hi[0] = max(hi[0], k0);
         lo[1] = min(lo[1], k1); hi[1] = max(hi[1], k1);
         lo[2] = min(lo[2], k2); hi[2] = max(hi[2], k2);
@@ -132,7 +154,7 @@ constexpr int kPrepWarps = 8;
 __global__ void __launch_bounds__(kPrepWarps * 32)
 k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             const double2 *__restrict__ angle_cs, int n_beams, MapGeom g,
-            ScoreFilteredWork *__restrict__ wk, TiledWork *tw)
+            ScoreFilteredWork *__restrict__ wk, TiledWork *tw, int staged_groups, int staged_blocks)
 {
     TraceScope trace_scope(kTrTilePrep);
     pdl_trigger();                              // k_score_tiled's blocks may be staged
@@ -197,8 +219,8 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     }
 
     // ---- up to two windows for the group
-    int cnt2[2] = {0, 0};
-    for (int pass = 0; pass < 2; pass++) {
+    int cnt2[kPrepPasses] = {};
+    for (int pass = 0; pass < kPrepPasses; pass++) {
         int x0 = todo ? b.x : 0x3fffffff, x1 = todo ? b.y : -0x3fffffff;
         int y0 = todo ? b.z : 0x3fffffff, y1 = todo ? b.w : -0x3fffffff;
 #pragma unroll
@@ -207,7 +229,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
         }
         const unsigned tm = __ballot_sync(0xffffffffu, todo);
-        const int slot = 2 * c + pass;
+        const int slot = kPrepPasses * c + pass;
         if (!tm) { if (lane == 0) { TileChunk tc; tc.x0 = 0; tc.y0 = 0; tc.count = 0; tc.pad = 0; tw->chunk[slot] = tc; } continue; }
         // fallback anchor when the span is too large: the middle beam still to place
         const int mid_lane = __fns(tm, 0, (__popc(tm) + 1) / 2);
@@ -261,29 +283,81 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     __threadfence();
 
     // ---- last warp: compact.  Non-empty windows in slot order with their work prefix ...
+    int n_win = 0;
     {
-        int base_m = 0, run = 0;
-        for (int s0 = 0; s0 < 2 * n_groups; s0 += 32) {
+        int base_m = 0, run = 0, runb = 0;
+        for (int s0 = 0; s0 < kPrepPasses * n_groups; s0 += 32) {
             const int sl = s0 + lane;
-            const int cv = sl < 2 * n_groups ? __ldcg(&tw->chunk[sl].count) : 0;
+            const int cv = sl < kPrepPasses * n_groups ? __ldcg(&tw->chunk[sl].count) : 0;
             const bool ne = cv > 0;
             const unsigned bm = __ballot_sync(0xffffffffu, ne);
             int inc = ne ? cv + kWindowCostBeams : 0;         // work weight of the window
+            int incb = cv;
             const int wv = inc;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o), ub = __shfl_up_sync(0xffffffffu, incb, o);
+                if (lane >= o) { inc += u; incb += ub; }
+            }
             if (ne) {
                 const int pos = base_m + __popc(bm & ((1u << lane) - 1));
                 tw->order[pos] = sl;
                 tw->cum[pos] = run + inc - wv;
+                tw->win[pos] = make_int4(__ldcg(&tw->chunk[sl].x0), __ldcg(&tw->chunk[sl].y0), cv, sl);
+                tw->bcum[pos] = runb + incb - cv;
             }
             base_m += __popc(bm);
             run += __shfl_sync(0xffffffffu, inc, 31);
+            runb += __shfl_sync(0xffffffffu, incb, 31);
         }
-        if (lane == 0) { tw->cum[base_m] = run; tw->n_chunks = base_m; }
+        if (lane == 0) { tw->cum[base_m] = run; tw->n_chunks = base_m; tw->bcum[base_m] = runb; }
+        n_win = base_m;
+    }
+    const int nf = atomicAdd(&tw->wide_run, 0), ns = atomicAdd(&tw->slow_run, 0);
+    // ... and the stage table of k_score_staged: tiled stages of kStageWindows windows, then the wide and the slow beams
+    // in stages of kStageWindows * 32 beams; per stage the units of the work line before it, and its first block
+    if (staged_groups > 0) {
+        __threadfence(); __syncwarp();
+        constexpr int SB = kStageWindows * kChunkBeams;
+        const int n_t = (n_win + kStageWindows - 1) / kStageWindows, n_w = (nf + SB - 1) / SB, n_s = (ns + SB - 1) / SB;
+        const int n_st = min(n_t + n_w + n_s, kMaxStages);
+        int run = 0;
+        for (int s0 = 0; s0 < n_st; s0 += 32) {
+            const int st = s0 + lane;
+            int kind = 0, first = 0, nb = 0;
+            if (st < n_st) {
+                if (st < n_t) { kind = kStTiled; first = st * kStageWindows; nb = __ldcg(&tw->bcum[min(first + kStageWindows, n_win)]) - __ldcg(&tw->bcum[first]); }
+                else if (st < n_t + n_w) { kind = kStWide; first = (st - n_t) * SB; nb = min(SB, nf - first); }
+                else { kind = kStSlow; first = (st - n_t - n_w) * SB; nb = min(SB, ns - first); }
+            }
+            int units = st < n_st ? nb * stage_weight(kind) + stage_setup(kind) : 0;
+            const int own = units;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, units, o); if (lane >= o) units += u; }
+            if (st < n_st) tw->stage[st] = make_int4(kind, first, nb, run + units - own);
+            run += __shfl_sync(0xffffffffu, units, 31);
+        }
+        __threadfence(); __syncwarp();
+        if (lane == 0) {
+            tw->n_stages = n_st; tw->u_total = run;
+            const int aligned = staged_blocks >= 2 * n_st ? 1 : 0;
+            tw->aligned = aligned;
+            int first = 0;
+            for (int st = 0; st < n_st; st++) {            // proportional, at least one block each, by cumulative rounding
+                const int4 sg = tw->stage[st];
+                const int u1 = sg.w + sg.z * stage_weight(sg.x) + stage_setup(sg.x);
+                int next = st == n_st - 1 ? staged_blocks : (int)(((long long)u1 * staged_blocks + run / 2) / max(run, 1));
+                next = max(next, first + 1);
+                next = min(next, staged_blocks - (n_st - 1 - st));
+                tw->sfirst[st] = first;
+                first = next;
+            }
+            tw->sfirst[n_st] = staged_blocks;
+        }
     }
     if (lane == 0) {
-        wk->nf = atomicAdd(&tw->wide_run, 0); wk->ns = atomicAdd(&tw->slow_run, 0);
+        wk->nf = nf; wk->ns = ns;
+        tw->stat_wide = nf; tw->stat_slow = ns;
         // consumed: reset the cloud bounds for the next frame's k_motion, and the per-frame counters
         for (int q = 0; q < 3; q++) { tw->bounds[2 * q] = 0x7fffffff; tw->bounds[2 * q + 1] = (int)0x80000000; }
         tw->wide_run = 0; tw->slow_run = 0; tw->done = 0;
@@ -713,7 +787,7 @@ static int score_tiled_setup(int device)
 
 // the second-generation kernel (pf_score_staged.cuh) has the same signature
 typedef void (*StagedKernel)(const CUtensorMap, const int8_t *, MapGeom, const float *, const float *, const float *, int,
-                             const StepParams *, const float *, const TiledWork *, int *, int *);
+                             const StepParams *, const float *, const TiledWork *, const ScoreFilteredWork *, const float4 *, int *, int *);
 
 // returns the number of kernels launched, or -1.  partial: score_tiled_rows()*n ints.
 // With an auxiliary stream the wide/slow-beam kernel (k_score_fast) runs NEXT TO the tiled kernel
@@ -727,27 +801,39 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                               cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                               LapRec *laps = nullptr, StagedKernel staged = nullptr, int staged_threads = 0, size_t staged_smem = 0,
-                              int staged_particles = 1024)
+                              int staged_particles = 1024, float4 *pcs = nullptr)
 {
     int nl = 4;
     if (!bounds_valid) {   // poses were not produced by k_motion this frame (test hooks): recompute
         k_bounds_reset<<<1, 32, 0, stream>>>(tw);
-        k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw, partial);
+        k_cloud_bounds<<<min(148, (n + 255) / 256), 256, 0, stream>>>(x, y, th, n, tw, partial, pcs);
         nl += 2;
     }
     const int n_prep_groups = (n_beams + kChunkBeams - 1) / kChunkBeams;
+    // k_score_staged: one block per SM; small filters get fewer blocks (a few beams of one group each at least)
+    const int sgroups = staged ? (n + staged_particles - 1) / staged_particles : 0;
+    const int gs = staged ? min(tiled_grid, max(1, ((n + 1023) / 1024) * 8)) : 0;
     launch_k(bounds_valid, k_tile_prep, dim3((n_prep_groups + kPrepWarps - 1) / kPrepWarps), dim3(kPrepWarps * 32), 0, stream,
-             scan, angle, angle_cs, n_beams, g, wk, tw);                  // dependent of k_motion when it ran just before
+             scan, angle, angle_cs, n_beams, g, wk, tw, sgroups, gs);                  // dependent of k_motion when it ran just before
     if (laps) laps->mark(stream, kLapTilePrep);
+    const int nblk = (n + 255) / 256;
+    if (staged) {
+        // one kernel scores the whole scan (tiled, wide and slow beams): stage-major slices, one block per SM; small filters
+        // get fewer blocks (a few beams of one group each at least)
+        if (ev0) cudaEventRecord(ev0, stream);
+        launch_k(true, staged, dim3(gs), dim3(staged_threads), staged_smem, stream, tmap, grid, g, x, y, th, n, scan, angle, tw, wk, pcs, partial, counters);
+        if (ev1) cudaEventRecord(ev1, stream);
+        if (laps) laps->mark(stream, kLapScoreTiled);
+        k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, 1, n, gidx0, fit, blk_min, blk_maxkey, x, y, th, ext_local, counters + 4, xc, scan);
+        if (laps) laps->mark(stream, kLapCombine);
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        return nl - 1;
+    }
     if (aux) { cudaEventRecord(ev_fork, stream); cudaStreamWaitEvent(aux, ev_fork, 0); }
     // one full wave; small filters get fewer blocks (an item is the smallest share)
     const int gt = min(tiled_grid, ((n + kTiledGroup - 1) / kTiledGroup) * kMaxChunks);
     if (ev0) cudaEventRecord(ev0, stream);
-    if (staged) {
-        // stage-major slices, one block per SM; small filters get fewer blocks (a few beams of one group each at least)
-        const int gs = min(tiled_grid, max(1, ((n + staged_particles - 1) / staged_particles) * 8));
-        launch_k(true, staged, dim3(gs), dim3(staged_threads), staged_smem, stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
-    } else if (tiled_threads() == 512)
+    if (tiled_threads() == 512)
         launch_k(true, k_score_tiled<512, 2>, dim3(gt), dim3(512), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
     else
         launch_k(true, k_score_tiled<256, 4>, dim3(gt), dim3(256), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
@@ -758,7 +844,6 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                                                               partial + (size_t)n, counters);
     if (laps) laps->mark(stream, kLapScoreFast);
     if (aux) { cudaEventRecord(ev_join, aux); cudaStreamWaitEvent(stream, ev_join, 0); }
-    const int nblk = (n + 255) / 256;
     k_score_combine_rows<<<nblk, 256, 0, stream>>>(partial, score_tiled_rows(), n, gidx0, fit, blk_min, blk_maxkey,
                                                    x, y, th, ext_local, counters + 4, xc, scan);
     if (laps) laps->mark(stream, kLapCombine);

@@ -71,6 +71,7 @@ struct pfslam_engine {
     int *score_partial = nullptr;
     TiledWork *twork = nullptr;
     double2 *angle_cs = nullptr;
+    float4 *pcs = nullptr;         // {x, y, cos(theta), sin(theta)} per particle, for the staged scorer
     bool prefix_fused = false;
     bool resample_follows_weights = false;   // k_resample is launched right after k_weights_scan on the same stream
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
@@ -205,7 +206,7 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->tiles_local);
     if (e->tiles_all != e->tiles_local) cudaFree(e->tiles_all);
     cudaFree(e->pose_all); cudaFree(e->prefix); cudaFree(e->res); cudaFree(e->counters);
-    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->angle_cs); cudaFree(e->sp);
+    cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->pcs); cudaFree(e->angle_cs); cudaFree(e->sp);
     cudaFree(e->kd); cudaFree(e->kds); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
     cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index); cudaFree(e->kd_claim);
     for (int r = 0; r < kMaxRanks; r++) if (e->peer_ipc[r] && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
@@ -295,6 +296,8 @@ static int engine_alloc(pfslam_engine *e)
     CUDA_TRY(cudaMalloc(&e->fwork, sizeof(ScoreFilteredWork)));
     CUDA_TRY(cudaMalloc(&e->score_partial, sizeof(int) * (size_t)score_tiled_rows() * n));
     CUDA_TRY(cudaMalloc(&e->twork, sizeof(TiledWork)));
+    CUDA_TRY(cudaMalloc(&e->pcs, sizeof(float4) * (size_t)n));
+    CUDA_TRY(cudaMemsetAsync(e->pcs, 0, sizeof(float4) * (size_t)n, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->twork, 0, sizeof(TiledWork), e->stream));
     CUDA_TRY(cudaMalloc(&e->sp, sizeof(StepParams)));
     CUDA_TRY(cudaMemsetAsync(e->sp, 0, sizeof(StepParams), e->stream));
@@ -591,7 +594,7 @@ static int ph_motion(pfslam_engine *e, int32_t frame)
     // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
     k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
                                                          xc.snap, xc.snap_stride, xc.parity_mask, xc.snap_aos, e->score_partial,
-                                                         e->io_capture ? e->h_scan_dev : nullptr, e->scan, e->cfg.n_beams);
+                                                         e->io_capture ? e->h_scan_dev : nullptr, e->scan, e->cfg.n_beams, e->pcs);
     if (e->laps_on) e->laps.mark(e->stream, kLapMotion);
     e->bounds_valid = true;
     e->launches++;
@@ -629,7 +632,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
                                     e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->tiled_grid, e->stream, ev0, ev1,
                                     use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr,
                                     e->staged ? staged_kernel() : nullptr, staged_threads(), staged_smem_bytes(),
-                                    staged_threads() * (staged_threads() == 1024 ? 2 : 4));
+                                    staged_threads() * (staged_threads() == 1024 ? 2 : 4), e->pcs);
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
@@ -1121,6 +1124,7 @@ static void copy_result(const FrameResult *r, pfslam_frame_result *out)
     out->exchange_timeout = r->xchg_timeout;
     out->resample_count = r->resample_count;
     out->wait_extrema_ns = r->wait_ext_ns; out->wait_tiles_ns = r->wait_tiles_ns;
+    out->n_windows = r->n_windows; out->n_wide_beams = r->n_wide;
 }
 
 int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)

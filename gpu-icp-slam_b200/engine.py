@@ -53,6 +53,7 @@ class FrameResult(C.Structure):
         ("n_slow_evals", C.c_int32), ("kd_size", C.c_int32), ("kd_inserted", C.c_int32),
         ("exchange_timeout", C.c_int32), ("resample_count", C.c_int32),
         ("wait_extrema_ns", C.c_int32), ("wait_tiles_ns", C.c_int32),
+        ("n_windows", C.c_int32), ("n_wide_beams", C.c_int32),
     ]
 
     def as_dict(self):

@@ -78,6 +78,8 @@ typedef struct pfslam_frame_result {
     int32_t resample_count;      /* steps that resampled so far (reset by the explicit-pose test entry points) */
     int32_t wait_extrema_ns;     /* sharded engines: time this rank's step kernels have spent waiting for the peers' */
     int32_t wait_tiles_ns;       /*   extrema / tile sums so far (nanoseconds, accumulated; wraps after ~2 s of waiting) */
+    int32_t n_windows;           /* tiled scorer: shared-memory windows placed for this frame's scan ... */
+    int32_t n_wide_beams;        /* ... and beams whose hit box over the cloud fits none (scored through global memory) */
 } pfslam_frame_result;
 
 /* ---- life cycle: particleFilterInit(Scene*) / particleFilterFree(), kernel.cu:107-178 ---- */

@@ -42,3 +42,9 @@ with g.ParticleFilter(n) as pf:
         print("  %-26s mean %7.2f us  max %7.2f us; pieces/block %.1f, stage loads/block %.1f" % (
             "block lifetime", (t[:, 8] - t[:, 0]).mean() / 1e3, (t[:, 8] - t[:, 0]).max() / 1e3, t[:, 9].mean(), t[:, 10].mean()))
         print("  kernel span (first entry -> last exit) %.2f us" % ((t[:, 8].max() - t0) / 1e3))
+        life = (t[:, 8] - t[:, 0]) / 1e3
+        order = np.argsort(-life)
+        print("  slowest / fastest blocks: (block, lifetime us, gather us, pieces, last stage, kind, beams in stage, slice units)")
+        for b in list(order[:8]) + list(order[-4:]):
+            w = int(ts[b, 11])
+            print("   %4d  %6.1f  %6.1f  %2d   stage %2d kind %d beams %3d units %d" % (b, life[b], t[b, 5] / 1e3, int(t[b, 9]), w & 255, (w >> 8) & 255, (w >> 16) & 0xffff, w >> 32))

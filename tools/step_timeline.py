@@ -29,13 +29,14 @@ with g.ParticleFilter(n) as pf:
         f += 1
         pf.synchronize()
         engine.debug_trace(True)
-        pf.step(sc[1 + (f - 1) % last], f)            # the host-API graph (scan pull + result publish inside)
+        r = pf.step(sc[1 + (f - 1) % last], f)        # the host-API graph (scan pull + result publish inside)
         pf.synchronize()
         tr = engine.debug_trace(True, read=True)
         t_first = min(a for a, _ in tr.values())
         for name, (a, b) in tr.items():
             rows.setdefault(name, []).append(((a - t_first) / 1e3, (b - t_first) / 1e3))
     engine.debug_trace(False)
+    print("last frame: %d windows, %d wide beams, %d exact re-evaluations, resampled %d" % (r.n_windows, r.n_wide_beams, r.n_slow_evals, r.resampled))
     print("| kernel | first block in (us) | last block out (us) | span (us) |")
     print("|---|---|---|---|")
     for name, v in sorted(rows.items(), key=lambda kv: np.mean([a for a, _ in kv[1]])):
