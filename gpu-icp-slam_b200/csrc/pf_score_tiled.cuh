@@ -338,22 +338,64 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             run += __shfl_sync(0xffffffffu, units, 31);
         }
         __threadfence(); __syncwarp();
-        if (lane == 0) {
-            tw->n_stages = n_st; tw->u_total = run;
-            const int aligned = staged_blocks >= 2 * n_st ? 1 : 0;
-            tw->aligned = aligned;
-            int first = 0;
-            for (int st = 0; st < n_st; st++) {            // proportional, at least one block each, by cumulative rounding
+        // Blocks per stage: proportional to the stage's units, at least one; the blocks left over by rounding down go,
+        // one at a time, to the stage with the most units per block (lane l keeps stages l, l + 32, ...).
+        const int aligned = staged_blocks >= 2 * n_st ? 1 : 0;
+        constexpr int kPer = kMaxStages / 32;
+        int su[kPer], sc[kPer];
+        int used = 0;
+#pragma unroll
+        for (int q = 0; q < kPer; q++) {
+            const int st = lane + 32 * q;
+            su[q] = 0; sc[q] = 0;
+            if (st < n_st) {
                 const int4 sg = tw->stage[st];
-                const int u1 = sg.w + sg.z * stage_weight(sg.x) + stage_setup(sg.x);
-                int next = st == n_st - 1 ? staged_blocks : (int)(((long long)u1 * staged_blocks + run / 2) / max(run, 1));
-                next = max(next, first + 1);
-                next = min(next, staged_blocks - (n_st - 1 - st));
-                tw->sfirst[st] = first;
-                first = next;
+                su[q] = sg.z * stage_weight(sg.x) + stage_setup(sg.x);
+                sc[q] = max(1, (int)((long long)su[q] * staged_blocks / max(run, 1)));
             }
-            tw->sfirst[n_st] = staged_blocks;
+            used += sc[q];
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+        for (int it = 0; aligned && used != staged_blocks && it < 4 * kMaxStages; it++) {
+            // more blocks to hand out: the stage with the largest units / blocks; too many (the "at least one"s): take
+            // one from the stage that suffers least, i.e. the smallest units / (blocks - 1) among those with > 1
+            const bool give = used < staged_blocks;
+            float best = give ? -1.0f : 3.0e38f; int best_st = -1;
+#pragma unroll
+            for (int q = 0; q < kPer; q++) {
+                const int st = lane + 32 * q;
+                if (st >= n_st) continue;
+                if (give) { const float v = (float)su[q] / (float)sc[q]; if (v > best) { best = v; best_st = st; } }
+                else if (sc[q] > 1) { const float v = (float)su[q] / (float)(sc[q] - 1); if (v < best) { best = v; best_st = st; } }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int os = __shfl_xor_sync(0xffffffffu, best_st, o);
+                const bool take = os >= 0 && (best_st < 0 || (give ? (ob > best || (ob == best && os < best_st)) : (ob < best || (ob == best && os < best_st))));
+                if (take) { best = ob; best_st = os; }
+            }
+            if (best_st < 0) break;
+#pragma unroll
+            for (int q = 0; q < kPer; q++) if (lane + 32 * q == best_st) sc[q] += give ? 1 : -1;
+            used += give ? 1 : -1;
+        }
+        // first block of every stage = exclusive prefix of the counts in stage order
+        {
+            int base = 0;
+#pragma unroll
+            for (int q = 0; q < kPer; q++) {
+                int v = sc[q];
+                const int own = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                const int st = lane + 32 * q;
+                if (st < n_st) tw->sfirst[st] = base + v - own;
+                base += __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        if (lane == 0) { tw->n_stages = n_st; tw->u_total = run; tw->aligned = aligned; tw->sfirst[n_st] = staged_blocks; }
     }
     if (lane == 0) {
         wk->nf = nf; wk->ns = ns;
