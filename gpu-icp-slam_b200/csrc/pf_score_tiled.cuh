@@ -463,7 +463,6 @@ __host__ __device__ constexpr uint32_t skew_selector(int m)
 
 struct TiledSmem {
     alignas(128) int8_t stage[kTileBytes];
-    alignas(16) int8_t skew[kSkewBytes];
     alignas(16) float4 cst[2][kChunkBeams];
     uint2 queue[kTiledQueueCap];              // {particle << 8 | window slot, mask of uncertain beams}
     int acc[kTiledGroup];
@@ -486,11 +485,15 @@ __global__ void __launch_bounds__(THREADS, (PPT == 4 ? 3 : 2))
 k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
               const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
               const StepParams *__restrict__ sp, const float *__restrict__ angle,
-              const TiledWork *__restrict__ tw, int *__restrict__ acc_row, int *__restrict__ counters)
+              const TiledWork *__restrict__ tw, const float4 *__restrict__ pcs, int *__restrict__ acc_row, int *__restrict__ counters)
 {
+    TraceScope trace_scope(kTrScore);
     const float *__restrict__ scan = sp->scan;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
+    // the gather copy of the window is STATIC shared memory: its address is a link-time constant, so the gather's LDS
+    // carries it as an immediate and the loop needs no base add
+    __shared__ __align__(16) int8_t s_skew[kSkewBytes];
     const int tid = threadIdx.x;
     pdl_wait();                                 // k_tile_prep's window table
     const int n_chunks = tw->n_chunks;
@@ -598,11 +601,9 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             for (int k = 0; k < PPT; k++) {
                 // lanes past the end take a copy of the last particle (results discarded), so every
                 // evaluation stays inside the staged window
-                const int p = min(grp * kTiledGroup + tid + k * THREADS, n - 1);
-                px[k] = x[p]; py[k] = y[p];
-                float sn, cs;
-                sincosf(th[p], &sn, &cs);
-                cc[k] = make_float2(cs, cs); ss[k] = make_float2(sn, sn);
+                const float4 v = pcs[min(grp * kTiledGroup + tid + k * THREADS, n - 1)];   // {x, y, cos, sin} from k_motion
+                px[k] = v.x; py[k] = v.y;
+                cc[k] = make_float2(v.z, v.z); ss[k] = make_float2(v.w, v.w);
                 acc[k] = 0;
             }
         }
@@ -632,7 +633,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
 #pragma unroll
             for (int i = 0; i < 4; i++) { const uint4 v = src[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
             w[16] = 0u;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(sm.skew + r * kSkewPitch + h * 68);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_skew + r * kSkewPitch + h * 68);
             dst[0] = w[0];
 #pragma unroll
             for (int m = 1; m < 17; m++) dst[m] = prmt(w[m - 1], w[m], skew_selector(m));
@@ -643,7 +644,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
             mbar_expect_tx(&sm.bar, kTileBytes);
             tma_load_2d(sm.stage, &tmap, wn.y, wn.x, &sm.bar);
         }
-        const int8_t *tile = sm.skew;
+        const int8_t *tile = s_skew;
         unsigned um[PPT];
 #pragma unroll
         for (int k = 0; k < PPT; k++) um[k] = 0u;
@@ -661,13 +662,15 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
                 const uint32_t bx = __float_as_uint(t2.x), by = __float_as_uint(t2.y);
                 const uint32_t idx = prmt(bx, by, 0xBB26u);
                 const int v = (int)tile[idx + (idx >> 4)];
+                // guard band: bits 7..15 == 0 on either axis -> uncertain (the beam's bit; set at most once, so ADD == OR
+                // and the instruction can go to either math pipe), else add the cell.  LOP3 with predicate output, the
+                // second one and-ing into the first (LOP3.LUT.PAND): 2 instructions for both axes.
                 asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                    "mul.lo.u32 t, %2, 65536;\n\t"            // low 16 bits to the top: IMAD.SHL, off the ALU pipe
-                    "setp.lt.u32 p, t, 0x800000;\n\t"         // bits 7..15 == 0  <=>  (b << 16) < (128 << 16)
-                    "mul.lo.u32 t, %3, 65536;\n\t"
-                    "setp.lt.or.u32 p, t, 0x800000, p;\n\t"
-                    "@p or.b32 %0, %0, %4;\n\t"
-                    "@!p add.s32 %1, %1, %5;\n\t}"
+                    "and.b32 t, %2, 0xFF80;\n\t"
+                    "setp.ne.u32 p, t, 0;\n\t"
+                    "lop3.and.b32 t|p, %3, 0xFF80, 0, 0xC0, p;\n\t"
+                    "@!p add.u32 %0, %0, %4;\n\t"
+                    "@p add.s32 %1, %1, %5;\n\t}"
                     : "+r"(um[k]), "+r"(acc[k]) : "r"(bx), "r"(by), "r"(bit), "r"(v));
             }
             bit <<= 1;
@@ -876,9 +879,9 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
     const int gt = min(tiled_grid, ((n + kTiledGroup - 1) / kTiledGroup) * kMaxChunks);
     if (ev0) cudaEventRecord(ev0, stream);
     if (tiled_threads() == 512)
-        launch_k(true, k_score_tiled<512, 2>, dim3(gt), dim3(512), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+        launch_k(true, k_score_tiled<512, 2>, dim3(gt), dim3(512), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, pcs, partial, counters);
     else
-        launch_k(true, k_score_tiled<256, 4>, dim3(gt), dim3(256), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, partial, counters);
+        launch_k(true, k_score_tiled<256, 4>, dim3(gt), dim3(256), sizeof(TiledSmem), stream, tmap, grid, g, x, y, th, n, scan, angle, tw, pcs, partial, counters);
     if (ev1) cudaEventRecord(ev1, stream);
     if (laps) laps->mark(stream, kLapScoreTiled);
     dim3 gf((n + kFastThreads - 1) / kFastThreads, kFastSlices + 1);          // last row = slow beams

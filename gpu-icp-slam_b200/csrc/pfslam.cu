@@ -77,7 +77,7 @@ struct pfslam_engine {
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
-    bool staged = true;            // scorer generation: k_score_staged (default) or k_score_tiled (PFSLAM_TILED_KERNEL=old)
+    bool staged = false;           // scorer generation: k_score_tiled (default) or k_score_staged (PFSLAM_TILED_KERNEL=staged)
     int tiled_grid = 0;            // k_score_tiled grid: SMs x resident blocks per SM
     // pinned host staging
     float *h_scan = nullptr, *h_scan_dev = nullptr;     // pinned + mapped: host pointer, device alias
@@ -424,7 +424,10 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
     if (ce != cudaSuccess) { pfslam_destroy(e); return set_error(PFSLAM_ERR_CUDA, "aux stream: %s", cudaGetErrorString(ce)); }
     { const char *no = getenv("PFSLAM_NO_OVERLAP"); e->overlap = !(no && atoi(no) != 0); }
-    { const char *tk = getenv("PFSLAM_TILED_KERNEL"); e->staged = !(tk && strcmp(tk, "old") == 0); }
+    // scorer generation: k_score_tiled (3 blocks per SM, one window per block at a time) is the default -- inside the step
+    // graph it still finishes ~10 us ahead of k_score_staged (1 block per SM, 5 windows resident, all beams in one kernel),
+    // whose block-wide stage loads nothing else on the SM can hide; PFSLAM_TILED_KERNEL=staged selects the latter
+    { const char *tk = getenv("PFSLAM_TILED_KERNEL"); e->staged = tk && strcmp(tk, "staged") == 0; }
     { const char *dg = getenv("PFSLAM_STAGED_DEBUG"); const int v = dg ? atoi(dg) : 0; cudaMemcpyToSymbol(g_staged_dbg, &v, sizeof v); }
     int rc = engine_alloc(e);
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
