@@ -371,7 +371,8 @@ def run_ours(args):
     sync_all()
     scans, order, scans_dev = scans[PW:], order[PW:], scans_dev[PW:]
     eng0 = pf.engine if world > 1 else pf
-    resample_count0 = eng0.fetch_result().resample_count
+    r0 = eng0.fetch_result()
+    resample_count0, wait0 = r0.resample_count, (r0.wait_extrema_ns, r0.wait_tiles_ns)
 
     # ---- `value`: K steps, inputs resident in HBM, device time per step by CUDA events on the launch
     # stream, L2 flushed (256 MiB memset, untimed) between steps
@@ -391,7 +392,10 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = pf.launch_count - l0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    resampled_steps = eng0.fetch_result().resample_count - resample_count0
+    r1 = eng0.fetch_result()
+    resampled_steps = r1.resample_count - resample_count0
+    # time this rank's kernels spent waiting for the peers' extrema / tile sums, per step (in-kernel %globaltimer stamps)
+    wait_us = [((r1.wait_extrema_ns - wait0[0]) & 0xffffffff) / 1e3 / K, ((r1.wait_tiles_ns - wait0[1]) & 0xffffffff) / 1e3 / K]
 
     # back-to-back (no flush) for reference: the streaming steady state
     sync_all()
@@ -444,19 +448,40 @@ def run_ours(args):
             pf.step(scans[W + k], order[W + k])
     sync_all()
     e2e_s = time.perf_counter() - t0
+    # the streaming flavour of the same API (pfslam_submit / pfslam_wait, two frames in flight): every frame's scan still
+    # comes from host memory and every frame's result is read on the host; the host's launch latency overlaps the device
+    e2e_stream_s = None
+    if not kd:
+        try:
+            sync_all()
+            t0 = time.perf_counter()
+            pending = []
+            for k in range(K):
+                pending.append(eng0.submit(scans[W + k], order[W + k]))
+                if len(pending) >= 2:
+                    eng0.wait(pending.pop(0))
+            while pending:
+                eng0.wait(pending.pop(0))
+            sync_all()
+            e2e_stream_s = time.perf_counter() - t0
+        except Exception as ex:          # streaming needs the captured step
+            print("streaming e2e skipped: %s" % ex, file=sys.stderr)
 
     # max over ranks
-    t = torch.tensor([dev_ms, b2b_ms, e2e_s * 1e3, ker], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, b2b_ms, e2e_s * 1e3, ker, wait_us[0], wait_us[1], (e2e_stream_s or 0.0) * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, b2b_ms, e2e_ms, ker = [float(v) for v in t.tolist()]
+    dev_ms, b2b_ms, e2e_ms, ker, wait_ext_us, wait_tiles_us, e2e_stream_ms = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peak, peak_src = peaks()
         scale = world * n / 65536.0                      # 65 536-particle frame equivalents per frame
         alg_bytes = n * (N_BEAMS + 20) + 4 * N_BEAMS     # N*1101 + 4324 per launch (per GPU)
-        if kd:   # one 32-B node per tree level per (particle, beam): N*B*32*ceil(log2 kdSize)
-            alg_bytes = n * N_BEAMS * 32 * int(np.ceil(np.log2(max(r.kd_size, 2))))
+        kd_visits = None
+        if kd:   # one node per visit per (particle, beam), with the MEASURED mean visited-node count; the
+            # scorer's walk loads the 16-byte search shadow of a node (pf_kernels_kd.cuh), plus the 32-byte winner
+            kd_visits = eng.kd_mean_visits(4096)
+            alg_bytes = int(n * N_BEAMS * (16.0 * kd_visits + 32.0))
         achieved = alg_bytes / (ker * 1e-3) / 1e9
         traffic, traffic_src = (None, "") if kd else scorer_traffic()
         line = {
@@ -473,14 +498,23 @@ def run_ours(args):
                                     "in-kernel stores/loads over NVLink peer memory, whole step = 1 CUDA graph per rank" if args.exchange == "peer"
                                     else "3 NCCL all-gathers between the step's phases")}),
             "resampled_steps": int(resampled_steps),
+            "exchange_wait_us_per_step": ({"extrema": wait_ext_us, "tiles": wait_tiles_us,
+                                           "note": "max over ranks of the time the step's kernels spent in the two peer waits"} if world > 1 else None),
             "value_back_to_back": K / (b2b_ms * 1e-3) * scale,
             "wall_s_timed_region": t_wall,
             "e2e": {"value": K / (e2e_ms * 1e-3) * scale, "unit": UNIT,
-                    "h2d_bytes_per_step": 4 * N_BEAMS, "d2h_bytes_per_step": C.sizeof(g.FrameResult)},
+                    "h2d_bytes_per_step": 4 * N_BEAMS, "d2h_bytes_per_step": C.sizeof(g.FrameResult),
+                    "call": "pfslam_step (blocking): host scan in, host result out, one graph launch + one synchronisation per frame"},
+            "e2e_streaming": ({"value": K / (e2e_stream_ms * 1e-3) * scale, "unit": UNIT, "frames_in_flight": 2,
+                               "call": "pfslam_submit / pfslam_wait over the pinned scan ring (same copies, host launch latency overlapped)"}
+                              if e2e_stream_ms > 0 else None),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_score_kd" if kd else "k_score_tiled", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker, "kernel_launches_timed": n_prof,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kd_mean_visited_nodes_per_walk": kd_visits,
+                         "note": ("kd: node loads are served by L1/L2 (the tree is a few MB), so this algorithmic-byte rate is not "
+                                  "DRAM traffic and may exceed the HBM peak; the kernel is bound by divergent instruction issue (DESIGN.md 5.3)" if kd else None),
+                         "kernel_ms": ker, "kernel_launches_timed": n_prof,
                          "kernel_ms_isolated": float(np.mean([a for a, _ in iso_ms])),
                          "scoring_phase_ms_isolated": float(np.mean([b for _, b in iso_ms]))},
             "kernels_ms_serialised": {k: round(v[0], 5) for k, v in laps.items()},

@@ -8,7 +8,7 @@ orchestration.  There is no CPU fallback: using the engine without the built CUD
 from .engine import (  # noqa: F401
     Config, FrameResult, ParticleFilter, PfslamError, Scene, Lidar, lib_path, load_library,
     particleFilterInit, particleFilter, particleFilterFree, getPCData,
-    PATH_GRID2D, PATH_KD, SCORE_EXACT, SCORE_FILTERED, SCORE_TILED, QUIRKS_REFERENCE, QUIRK_Q1,
+    PATH_GRID2D, PATH_KD, SCORE_EXACT, SCORE_FILTERED, SCORE_TILED, QUIRKS_REFERENCE, QUIRK_Q1, RING_DEPTH,
 )
 from . import scans  # noqa: F401
 

@@ -104,14 +104,20 @@ struct FrameResult {
     int   resample_count;      // steps that resampled so far
     int   wait_ext_ns, wait_tiles_ns;   // accumulated peer-exchange wait times (block 0 / the last block of k_weights_scan)
     int   n_windows, n_wide;   // tiled scorer: windows placed / beams left to the global-memory path this frame
+    int   kd_overflow;         // kd path: 1 = more wall points in a scan than the point lists hold, 2 = node array full (sticky)
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
 // step can be replayed with new values (a 16-byte H2D copy node at the head of the graph)
+struct FrameResult;
 struct StepParams {
     const float *scan;   // this frame's ranges (device)
     int frame;           // frame number (seeds, kernel.cu:380, :434)
     int seq;             // step sequence number (peer-exchange flags and buffer parity, pf_xchg.cuh)
+    // host-API steps (pfslam_step / pfslam_submit): the slot of the pinned, device-mapped scan ring the first kernel
+    // pulls this frame's ranges from, and the slot of the result ring the last node publishes into; null otherwise
+    const float *scan_src;
+    FrameResult *res_host;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -142,8 +148,10 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
     // host API step (pfslam_step): the frame's scan is pulled from the pinned, device-mapped staging buffer by the
     // first kernel of the step (nobody reads the device copy before this grid has completed), so the step graph needs
     // no copy node for it
-    if (scan_src && blockIdx.x == gridDim.x - 1)
-        for (int j = threadIdx.x; j < n_beams; j += blockDim.x) scan_dst[j] = scan_src[j];
+    if (scan_src && blockIdx.x == gridDim.x - 1) {
+        const float *__restrict__ src = sp->scan_src;
+        if (src) for (int j = threadIdx.x; j < n_beams; j += blockDim.x) scan_dst[j] = src[j];
+    }
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,11 +190,12 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
 }
 
 // host API step: the frame result goes to the pinned, device-mapped result record from the last node of the graph
-__global__ void k_publish_result(const FrameResult *__restrict__ res, FrameResult *__restrict__ host_res)
+__global__ void k_publish_result(const FrameResult *__restrict__ res, const StepParams *__restrict__ sp)
 {
     TraceScope trace_scope(kTrPublish);
     const int *s = reinterpret_cast<const int *>(res);
-    int *d = reinterpret_cast<int *>(host_res);
+    int *d = reinterpret_cast<int *>(sp->res_host);
+    if (!d) return;
     for (int i = threadIdx.x; i < (int)(sizeof(FrameResult) / 4); i += blockDim.x) d[i] = s[i];
 }
 

@@ -259,6 +259,54 @@ k_score_kd(const KdNode *__restrict__ tree, const KdSearch *__restrict__ sh, con
     }
 }
 
+// Measurement only (bench.py's kd roofline line, SURVEY 8d "report with measured mean visited-node count"): the same
+// walk as kd_nn<>, counting the nodes it loads, over the first n_sample particles x all in-range beams.
+__global__ void __launch_bounds__(256)
+k_kd_count_visits(const KdNode *__restrict__ tree, const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
+                  int n_sample, const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
+                  unsigned long long *__restrict__ out /* [0] visits, [1] walks */)
+{
+    const float *__restrict__ scan = sp->scan;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    unsigned long long visits = 0, walks = 0;
+    if (p < n_sample) {
+        const float px = x[p], py = y[p], pth = th[p];
+        for (int j = warp; j < n_beams; j += 8) {
+            const float rot = __fadd_rn(__ldg(&angle[j]), pth);
+            const float r = __ldg(&scan[j]);
+            const float wx = __fmul_rn(r, cosf(rot)), wy = __fmul_rn(r, sinf(rot));
+            if (!(fabsf(wx) < kLidarRange && fabsf(wy) < kLidarRange)) continue;
+            const float qx = __fadd_rn(wx, px), qy = __fadd_rn(wy, py), qz = 0.0f;
+            KdNode t = kd_load(tree, 0);
+            float best2 = kd_dist2(qx, qy, qz, t.x, t.y, t.z), bestDist = __fsqrt_rn(best2);
+            int bestParent = t.parent, head = 0;
+            bool explored = false;
+            visits++; walks++;
+            for (;;) {
+                while (head >= 0) {
+                    t = kd_load(tree, head); visits++;
+                    const float d2 = kd_dist2(qx, qy, qz, t.x, t.y, t.z);
+                    if (d2 < best2) { const float d = __fsqrt_rn(d2); if (d < bestDist) { bestDist = d; best2 = d2; bestParent = t.parent; explored = false; } }
+                    const bool branch = t.axis == 0 ? qx < t.x : t.axis == 1 ? qy < t.y : t.axis == 2 ? qz < t.z : false;
+                    head = branch ? t.left : t.right;
+                }
+                if (explored || bestParent < 0) break;
+                const KdNode pn = kd_load(tree, bestParent); visits++;
+                bool branch = false; float hd = 0.0f;
+                if (pn.axis == 0) { branch = qx < pn.x; hd = fabsf(__fsub_rn(qx, pn.x)); }
+                if (pn.axis == 1) { branch = qy < pn.y; hd = fabsf(__fsub_rn(qy, pn.y)); }
+                if (pn.axis == 2) { branch = qz < pn.z; hd = fabsf(__fsub_rn(qz, pn.z)); }
+                if (!(hd < bestDist)) break;
+                head = !branch ? pn.left : pn.right;
+                explored = true;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { visits += __shfl_xor_sync(0xffffffffu, visits, o); walks += __shfl_xor_sync(0xffffffffu, walks, o); }
+    if (lane == 0) { atomicAdd(&out[0], visits); atomicAdd(&out[1], walks); }
+}
+
 // IEEE-only asin (Cephes asinf scheme): theta = asin(R[0][1]), kernel.cu:1079
 __device__ __forceinline__ float pf_asinf(float x)
 {
@@ -573,10 +621,14 @@ k_kd_insert(KdNode *tree, MapGeom g, KdState *__restrict__ ks, int cap, int kd_c
 }
 
 // publish the kd counters into the frame result
-__global__ void k_kd_finish(FrameResult *__restrict__ res, const KdState *__restrict__ ks, int *__restrict__ counters)
+__global__ void k_kd_finish(FrameResult *__restrict__ res, const KdState *__restrict__ ks, int *__restrict__ counters, int pc_cap, int kd_cap)
 {
     res->n_free = ks->n_free; res->n_wall = ks->n_wall; res->n_slow = 0;
     res->kd_size = ks->size; res->kd_ins = ks->n_ins;
+    // capacities are hard limits, not silent clamps: more wall points in one scan than the point lists hold, or a full
+    // node array, make the step fail (sticky, reported by pfslam_fetch_result / pfslam_step)
+    if (ks->n_wall > pc_cap) res->kd_overflow |= 1;
+    if (ks->size >= kd_cap) res->kd_overflow |= 2;
     counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
 }
 

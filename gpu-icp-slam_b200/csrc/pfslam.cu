@@ -80,9 +80,14 @@ struct pfslam_engine {
     bool staged = false;           // scorer generation: k_score_tiled (default) or k_score_staged (PFSLAM_TILED_KERNEL=staged)
     int tiled_grid = 0;            // k_score_tiled grid: SMs x resident blocks per SM
     // pinned host staging
-    float *h_scan = nullptr, *h_scan_dev = nullptr;     // pinned + mapped: host pointer, device alias
+    // pinned + device-mapped staging: slot 0 serves the blocking calls (upload_scan, fetch_result, ...), slots
+    // 1..kRing the streaming ring of pfslam_submit / pfslam_wait (host pointer, device alias)
+    float *h_scan = nullptr, *h_scan_dev = nullptr;
     FrameResult *h_res = nullptr, *h_res_dev = nullptr;
     bool io_capture = false;               // capturing the host-API flavour of the step graph
+    cudaEvent_t ring_ev[PFSLAM_RING_DEPTH] = {};
+    int ring_ticket[PFSLAM_RING_DEPTH] = {};   // ticket occupying the slot (0 = free)
+    int next_ticket = 1;
     long long launches = 0;
     // kd-tree point-cloud path
     KdNode *kd = nullptr; int kd_cap = 0;
@@ -92,11 +97,13 @@ struct pfslam_engine {
     int kd_walk = 1;                       // shadow format / visit body: 1 (default), 2 = branch-free visit (PFSLAM_KD_WALK=2)
     KdState *ks = nullptr;
     int *bits_blk = nullptr; int n_bits_blk = 0;
-    int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 4096;
+    int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 8192;
     float2 *kd_pts = nullptr; int *kd_nn_idx = nullptr, *kd_ins_index = nullptr;
     int *kd_claim = nullptr; int kd_stamp = 0;   // once-per-node-per-pass weight updates (k_kd_weights)
     bool kd_empty = true;                  // no tree yet (kdSize == 0, kernel.cu:1714)
     std::vector<KdNode> h_kd;
+    float *kd_q = nullptr; int *kd_qi = nullptr; int kd_q_cap = 0;    // pfslam_kd_nn's query / result buffers (grown on demand)
+    unsigned long long *kd_cnt = nullptr;
     // per-step parameters (device copy + pinned ring) and the captured step graph
     StepParams *sp = nullptr;
     StepParams *h_sp = nullptr;            // kParamSlots pinned slots
@@ -167,7 +174,7 @@ static int push_params(pfslam_engine *e, const float *scan, int frame)
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
     if (rc) return rc;
-    slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
+    slot->scan = scan; slot->frame = frame; slot->seq = e->seq; slot->scan_src = nullptr; slot->res_host = nullptr;
     CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
     e->cur = *slot;
     return param_slot_used(e);
@@ -209,6 +216,7 @@ int pfslam_destroy(pfslam_engine *e)
     cudaFree(e->fwork); cudaFree(e->score_partial); cudaFree(e->twork); cudaFree(e->pcs); cudaFree(e->angle_cs); cudaFree(e->sp);
     cudaFree(e->kd); cudaFree(e->kds); cudaFree(e->ks); cudaFree(e->bits_blk); cudaFree(e->free_cells); cudaFree(e->wall_cells);
     cudaFree(e->kd_pts); cudaFree(e->kd_nn_idx); cudaFree(e->kd_ins_index); cudaFree(e->kd_claim);
+    cudaFree(e->kd_q); cudaFree(e->kd_qi); cudaFree(e->kd_cnt);
     for (int r = 0; r < kMaxRanks; r++) if (e->peer_ipc[r] && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
     cudaFree(e->xreg);
     cudaFreeHost(e->h_sp);
@@ -218,6 +226,7 @@ int pfslam_destroy(pfslam_engine *e)
     if (e->graph_io_exec) cudaGraphExecDestroy(e->graph_io_exec);
     if (e->graph_io) cudaGraphDestroy(e->graph_io);
     cudaFreeHost(e->h_scan); cudaFreeHost(e->h_res);
+    for (auto ev : e->ring_ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     for (auto ev : e->laps.ev) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
@@ -320,8 +329,10 @@ static int engine_alloc(pfslam_engine *e)
         CUDA_TRY(cudaMalloc(&e->kd_claim, sizeof(int) * (size_t)e->kd_cap));
         CUDA_TRY(cudaMemsetAsync(e->kd_claim, 0, sizeof(int) * (size_t)e->kd_cap, e->stream));
     }
-    CUDA_TRY(cudaHostAlloc(&e->h_scan, sizeof(float) * e->cfg.n_beams, cudaHostAllocMapped));
-    CUDA_TRY(cudaHostAlloc(&e->h_res, sizeof(FrameResult), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&e->h_scan, sizeof(float) * e->cfg.n_beams * (PFSLAM_RING_DEPTH + 1), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(&e->h_res, sizeof(FrameResult) * (PFSLAM_RING_DEPTH + 1), cudaHostAllocMapped));
+    memset(e->h_res, 0, sizeof(FrameResult) * (PFSLAM_RING_DEPTH + 1));
+    for (auto &ev : e->ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(cudaHostGetDevicePointer(&e->h_scan_dev, e->h_scan, 0));
     CUDA_TRY(cudaHostGetDevicePointer(&e->h_res_dev, e->h_res, 0));
     // initial state: kernel.cu:122-132
@@ -477,7 +488,7 @@ int pfslam_set_params(pfslam_engine *e, const float *scan_dev, int32_t frame)
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
     if (rc) return rc;
-    slot->scan = scan_dev ? scan_dev : e->scan; slot->frame = frame; slot->seq = e->seq;
+    slot->scan = scan_dev ? scan_dev : e->scan; slot->frame = frame; slot->seq = e->seq; slot->scan_src = nullptr; slot->res_host = nullptr;
     CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
     e->cur = *slot;
     return param_slot_used(e);
@@ -973,7 +984,7 @@ static int kd_update_map(pfslam_engine *e)
         e->kd_size_ub = std::min(e->kd_cap, e->kd_size_ub + e->pc_cap);
         { int rc = kd_refresh_shadow(e, 0); if (rc) return rc; }
     }
-    k_kd_finish<<<1, 1, 0, e->stream>>>(e->res, e->ks, e->counters);
+    k_kd_finish<<<1, 1, 0, e->stream>>>(e->res, e->ks, e->counters, e->pc_cap, e->kd_cap);
     e->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
@@ -1048,7 +1059,7 @@ static int build_graph(pfslam_engine *e, bool with_io)
     e->in_capture = true; e->io_capture = with_io;       // with_io: k_motion pulls the scan from the mapped staging buffer
     int rc = run_phases(e, nullptr, 0);
     e->in_capture = false; e->io_capture = false;
-    if (with_io) k_publish_result<<<1, 32, 0, e->stream>>>(e->res, e->h_res_dev);
+    if (with_io) k_publish_result<<<1, 32, 0, e->stream>>>(e->res, e->sp);
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     e->launches = launches_before;
@@ -1081,13 +1092,16 @@ static bool graph_usable(const pfslam_engine *e)
     return e->use_graph && !e->prof_on && !e->laps_on && !e->graph_failed && e->cfg.path == PFSLAM_PATH_GRID2D;
 }
 
-// one replay of a captured step with this frame's {scan pointer, frame, seq} in its head copy node
-static int launch_graph(pfslam_engine *e, cudaGraphExec_t ge, cudaGraphNode_t pn, const float *scan, int32_t frame)
+// one replay of a captured step with this frame's parameters in its head copy node; io_slot >= 0: the slot of the pinned
+// scan / result rings the step pulls its scan from and publishes its result into
+static int launch_graph(pfslam_engine *e, cudaGraphExec_t ge, cudaGraphNode_t pn, const float *scan, int32_t frame, int io_slot = -1)
 {
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
     if (rc) return rc;
     slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
+    slot->scan_src = io_slot >= 0 ? e->h_scan_dev + (size_t)io_slot * e->cfg.n_beams : nullptr;
+    slot->res_host = io_slot >= 0 ? e->h_res_dev + io_slot : nullptr;
     CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ge, pn, e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaGraphLaunch(ge, e->stream));
     e->cur = *slot;
@@ -1130,41 +1144,91 @@ static void copy_result(const FrameResult *r, pfslam_frame_result *out)
     out->n_windows = r->n_windows; out->n_wide_beams = r->n_wide;
 }
 
+static int finish_result(pfslam_engine *e, const FrameResult *r, pfslam_frame_result *out);
+
 int pfslam_fetch_result(pfslam_engine *e, pfslam_frame_result *out)
 {
     if (!e || !out) return set_error(PFSLAM_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(e->cfg.device));
     CUDA_TRY(cudaMemcpyAsync(e->h_res, e->res, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    copy_result(e->h_res, out);
-    if (e->h_res->xchg_timeout)
+    return finish_result(e, e->h_res, out);
+}
+
+static int finish_result(pfslam_engine *e, const FrameResult *r, pfslam_frame_result *out)
+{
+    pfslam_frame_result tmp;
+    copy_result(r, out ? out : &tmp);
+    if (r->xchg_timeout)
         return set_error(PFSLAM_ERR_STATE, "peer exchange timed out (a shard stopped stepping, or the shards are out of step)");
+    if (r->kd_overflow & 1)
+        return set_error(PFSLAM_ERR_STATE, "kd map update: a scan produced more wall points than the point lists hold (%d)", e->pc_cap);
+    if (r->kd_overflow & 2)
+        return set_error(PFSLAM_ERR_STATE, "kd tree full: kd_capacity = %d nodes", e->kd_cap);
     return PFSLAM_OK;
+}
+
+static bool io_graph_ready(pfslam_engine *e)
+{
+    if (!(graph_usable(e) && (e->n_ranks == 1 || e->p2p_ready))) return false;
+    e->cur_xc = e->p2p_ready ? &e->xc_p2p : &e->xc_host;      // before the capture: the kernels take it by value
+    if (!e->graph_io_exec && build_graph(e, true) != 0) e->graph_failed = true;
+    return e->graph_io_exec != nullptr;
+}
+
+// Streaming input (the reference reads lidar->scans[frame] synchronously, main.cpp:199-206): the frame's scan goes into
+// a slot of a pinned, device-mapped ring, the step is ONE graph launch that pulls it from there and publishes its
+// result into the slot's result record; nothing blocks.  Up to PFSLAM_RING_DEPTH frames may be in flight, so a 40 Hz
+// producer never waits for the device and the device never waits for the host.
+int pfslam_submit(pfslam_engine *e, const float *scan, int32_t frame, int32_t *ticket)
+{
+    if (!e || !scan || !ticket) return set_error(PFSLAM_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (!io_graph_ready(e))
+        return set_error(PFSLAM_ERR_UNSUPPORTED, "streaming needs the captured 2D step (a non-default stream, the grid path, no profiling)");
+    const int t = e->next_ticket, sl = 1 + (t - 1) % PFSLAM_RING_DEPTH;
+    if (e->ring_ticket[sl - 1] != 0)
+        return set_error(PFSLAM_ERR_STATE, "scan ring full: %d frames in flight, pfslam_wait the oldest first", PFSLAM_RING_DEPTH);
+    memcpy(e->h_scan + (size_t)sl * e->cfg.n_beams, scan, sizeof(float) * e->cfg.n_beams);
+    e->seq++;
+    int rc = launch_graph(e, e->graph_io_exec, e->graph_io_param_node, e->scan, frame, sl);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(e->ring_ev[sl - 1], e->stream));
+    e->ring_ticket[sl - 1] = t;
+    e->next_ticket++;
+    *ticket = t;
+    return PFSLAM_OK;
+}
+
+int pfslam_wait(pfslam_engine *e, int32_t ticket, pfslam_frame_result *out)
+{
+    if (!e || ticket <= 0) return set_error(PFSLAM_ERR_ARG, "bad argument");
+    const int sl = 1 + (ticket - 1) % PFSLAM_RING_DEPTH;
+    if (e->ring_ticket[sl - 1] != ticket) return set_error(PFSLAM_ERR_STATE, "ticket %d is not in flight", ticket);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaEventSynchronize(e->ring_ev[sl - 1]));
+    e->ring_ticket[sl - 1] = 0;
+    return finish_result(e, e->h_res + sl, out);
 }
 
 int pfslam_step(pfslam_engine *e, const float *scan, int32_t frame, pfslam_frame_result *out)
 {
     int rc;
     if (!e || !scan) return set_error(PFSLAM_ERR_ARG, "null argument");
-    pfslam_frame_result tmp;
-    if (graph_usable(e) && (e->n_ranks == 1 || e->p2p_ready)) {
-        // host scan in, host result out: one graph launch (copies inside) and one synchronisation
-        CUDA_TRY(cudaSetDevice(e->cfg.device));
-        // earlier asynchronous work (pfslam_step_async, phase calls) may still be reading the staging buffers
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    bool ring_idle = true;
+    for (int t : e->ring_ticket) ring_idle = ring_idle && t == 0;
+    if (ring_idle && io_graph_ready(e)) {
+        // host scan in, host result out: one graph launch (scan pull and result publish inside) and one synchronisation
+        // (earlier asynchronous work -- pfslam_step_async, phase calls -- may still be reading staging slot 0)
         if (cudaStreamQuery(e->stream) != cudaSuccess) { cudaGetLastError(); CUDA_TRY(cudaStreamSynchronize(e->stream)); }
-        e->cur_xc = e->p2p_ready ? &e->xc_p2p : &e->xc_host;      // before the capture: the kernels take it by value
-        if (!e->graph_io_exec && build_graph(e, true) != 0) e->graph_failed = true;
-        if (e->graph_io_exec) {
-            memcpy(e->h_scan, scan, sizeof(float) * e->cfg.n_beams);
-            e->seq++;
-            if ((rc = launch_graph(e, e->graph_io_exec, e->graph_io_param_node, e->scan, frame))) return rc;
-            CUDA_TRY(cudaStreamSynchronize(e->stream));
-            copy_result(e->h_res, out ? out : &tmp);
-            if (e->h_res->xchg_timeout)
-                return set_error(PFSLAM_ERR_STATE, "peer exchange timed out (a shard stopped stepping, or the shards are out of step)");
-            return PFSLAM_OK;
-        }
+        memcpy(e->h_scan, scan, sizeof(float) * e->cfg.n_beams);
+        e->seq++;
+        if ((rc = launch_graph(e, e->graph_io_exec, e->graph_io_param_node, e->scan, frame, 0))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        return finish_result(e, e->h_res, out);
     }
+    pfslam_frame_result tmp;
     if ((rc = pfslam_upload_scan(e, scan))) return rc;
     if ((rc = pfslam_step_async(e, nullptr, frame))) return rc;
     if ((rc = pfslam_fetch_result(e, out ? out : &tmp))) return rc;
@@ -1301,15 +1365,38 @@ int pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_o
     if (!e || !q_xyz || !idx_out || n <= 0) return set_error(PFSLAM_ERR_ARG, "bad argument");
     if (e->cfg.path != PFSLAM_PATH_KD) return set_error(PFSLAM_ERR_STATE, "engine was not created with PFSLAM_PATH_KD");
     CUDA_TRY(cudaSetDevice(e->cfg.device));
-    float *dq = nullptr; int *di = nullptr;
-    CUDA_TRY(cudaMalloc(&dq, sizeof(float) * 3 * n));
-    cudaError_t ce = cudaMalloc(&di, sizeof(int) * n);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(dq, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, e->stream);
-    if (ce == cudaSuccess) { k_kd_nn<<<ceil_div(n, 128), 128, 0, e->stream>>>(e->kd, e->ks, dq, n, di); e->launches++; ce = cudaGetLastError(); }
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(idx_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost, e->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-    cudaFree(dq); cudaFree(di);
-    if (ce != cudaSuccess) return set_error(PFSLAM_ERR_CUDA, "kd_nn: %s", cudaGetErrorString(ce));
+    if (n > e->kd_q_cap) {
+        cudaFree(e->kd_q); cudaFree(e->kd_qi); e->kd_q = nullptr; e->kd_qi = nullptr; e->kd_q_cap = 0;
+        const int cap = std::max(n, 4096);
+        CUDA_TRY(cudaMalloc(&e->kd_q, sizeof(float) * 3 * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&e->kd_qi, sizeof(int) * (size_t)cap));
+        e->kd_q_cap = cap;
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->kd_q, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+    k_kd_nn<<<ceil_div(n, 128), 128, 0, e->stream>>>(e->kd, e->ks, e->kd_q, n, e->kd_qi);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(idx_out, e->kd_qi, sizeof(int) * n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PFSLAM_OK;
+}
+
+// measurement hook (bench.py's kd roofline line): mean number of tree nodes one NN walk of the scorer loads, measured
+// over the first n_sample particles x all in-range beams of the engine's current scan
+int pfslam_kd_mean_visits(pfslam_engine *e, int32_t n_sample, double *mean_visits)
+{
+    if (!e || !mean_visits) return set_error(PFSLAM_ERR_ARG, "null argument");
+    if (e->cfg.path != PFSLAM_PATH_KD || e->kd_empty) return set_error(PFSLAM_ERR_STATE, "no kd tree");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    n_sample = std::max(1, std::min(n_sample, e->n));
+    if (!e->kd_cnt) CUDA_TRY(cudaMalloc(&e->kd_cnt, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(e->kd_cnt, 0, 2 * sizeof(unsigned long long), e->stream));
+    k_kd_count_visits<<<ceil_div(n_sample, 32), 256, 0, e->stream>>>(e->kd, e->x, e->y, e->th, n_sample, e->sp, e->angle, e->cfg.n_beams, e->kd_cnt);
+    e->launches++;
+    unsigned long long h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, e->kd_cnt, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    *mean_visits = h[1] ? (double)h[0] / (double)h[1] : 0.0;
     return PFSLAM_OK;
 }
 

@@ -22,6 +22,7 @@ SCORE_EXACT, SCORE_FILTERED, SCORE_TILED = 0, 1, 2
 QUIRK_Q1 = 1
 QUIRKS_REFERENCE = QUIRK_Q1
 IPC_HANDLE_BYTES = 64
+RING_DEPTH = 8
 LAP_COUNT = 10
 BUF_EXTREMA_LOCAL, BUF_EXTREMA_ALL, BUF_TILES_LOCAL, BUF_TILES_ALL, BUF_POSE_LOCAL, BUF_POSE_ALL, BUF_SCAN = range(7)
 
@@ -77,6 +78,8 @@ _SIGS = {
     "pfslam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FrameResult)]),
     "particleFilterStep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
     "pfslam_step_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "pfslam_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "pfslam_wait": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(FrameResult)]),
     "pfslam_fetch_result": (C.c_int, [C.c_void_p, C.POINTER(FrameResult)]),
     "pfslam_upload_scan": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pfslam_phase_motion": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -104,6 +107,7 @@ _SIGS = {
     "pfslam_kd_nn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pfslam_get_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "pfslam_set_kd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "pfslam_kd_mean_visits": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "pfslam_kd_icp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfslam_launch_count": (C.c_int64, [C.c_void_p]),
     "pfslam_profile_score": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -287,6 +291,19 @@ class ParticleFilter:
         self._check(self._lib.pfslam_step(self._h, s.ctypes.data, int(frame), C.byref(out)))
         return out
 
+    def submit(self, scan, frame):
+        """streaming step: enqueue one frame (scan copied into the pinned ring), returns a ticket; up to RING_DEPTH in flight"""
+        s = _f32(scan, self.n_beams)
+        t = C.c_int32()
+        self._check(self._lib.pfslam_submit(self._h, s.ctypes.data, int(frame), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        """blocks until the submitted step's result is on the host"""
+        out = FrameResult()
+        self._check(self._lib.pfslam_wait(self._h, int(ticket), C.byref(out)))
+        return out
+
     def step_async(self, frame, scan_dev_ptr=None):
         self._check(self._lib.pfslam_step_async(self._h, scan_dev_ptr, int(frame)))
 
@@ -415,6 +432,12 @@ class ParticleFilter:
         a, b, out = _f32(robot_prev, 3), _f32(start, 3), np.zeros(3, np.float32)
         self._check(self._lib.pfslam_kd_icp(self._h, s.ctypes.data, a.ctypes.data, b.ctypes.data, out.ctypes.data))
         return out
+
+    def kd_mean_visits(self, n_sample=2048):
+        """mean tree nodes loaded per NN walk of the scorer (measured on the current scan and cloud)"""
+        v = C.c_double()
+        self._check(self._lib.pfslam_kd_mean_visits(self._h, int(n_sample), C.byref(v)))
+        return v.value
 
     def set_kd(self, nodes):
         a = np.ascontiguousarray(nodes, dtype=np.int32).reshape(-1, 8)

@@ -96,6 +96,15 @@ int  pfslam_set_stream(pfslam_engine *e, void *cuda_stream);
  * on the host.  particleFilterStep is the name BASELINE.json uses for the same call. */
 int  pfslam_step(pfslam_engine *e, const float *scan, int32_t frame, pfslam_frame_result *out);
 int  particleFilterStep(pfslam_engine *e, const float *scan, int32_t frame, float pose_out[3]);
+/* Streaming variant of pfslam_step (the input side of src/main.cpp:199-206 + src/lidar.cpp without the blocking): the
+ * scan is copied into a slot of a pinned ring and the step is enqueued -- one graph launch that pulls the scan from the
+ * slot and publishes the frame result next to it; pfslam_wait blocks until that step's result is on the host.  Up to
+ * PFSLAM_RING_DEPTH steps may be in flight (PFSLAM_ERR_STATE when the ring is full); tickets complete in order.
+ * Grid path on a non-default stream only (PFSLAM_ERR_UNSUPPORTED otherwise). */
+#define PFSLAM_RING_DEPTH 8
+int  pfslam_submit(pfslam_engine *e, const float *scan, int32_t frame, int32_t *ticket);
+int  pfslam_wait(pfslam_engine *e, int32_t ticket, pfslam_frame_result *out);
+
 /* Same step without any host synchronisation: the scan is taken from DEVICE memory and the result
  * stays on the device until pfslam_fetch_result(). */
 int  pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame);
@@ -141,6 +150,9 @@ int  pfslam_kd_nn(pfslam_engine *e, const float *q_xyz, int32_t n, int32_t *idx_
 /* getPCData's kd part (kernel.cu:810-811): copies up to cap nodes, returns the tree size */
 int  pfslam_get_kd(pfslam_engine *e, void *nodes_out, int32_t cap, int32_t *n_nodes);
 int  pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes);
+/* measurement hook (bench.py's kd roofline line): mean number of tree nodes one NN walk of the scorer loads,
+ * over the first n_sample particles x all in-range beams of the current scan */
+int  pfslam_kd_mean_visits(pfslam_engine *e, int32_t n_sample, double *mean_visits);
 /* ICP refinement alone (transformPointICP, kernel.cu:993-1093): one point-to-point step of `scan` against
  * the tree.  `robot_prev` is the pose the targets are built from (the global robotPos the reference reads
  * in kernGetWallsKD, kernel.cu:1011), `start` the pose that is corrected (the best particle's). */

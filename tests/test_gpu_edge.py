@@ -133,3 +133,31 @@ def test_headless_driver_kd_path_over_reference_symbols(tmp_path, scans):
         kd = pf.get_kd()
     assert "kd_nodes %d " % len(kd) in r.stdout, r.stdout
     assert "kd_weight_sum %.0f" % float(kd[:, 7].copy().view(np.float32).astype(np.float64).sum()) in r.stdout, r.stdout
+
+
+def test_streaming_ring_equals_blocking_step(scans):
+    """pfslam_submit / pfslam_wait (pinned scan ring, up to 8 frames in flight) == pfslam_step, frame for frame, bit for bit;
+    a full ring is refused, an unknown ticket too"""
+    import gpu_icp_slam_b200 as g
+    n = 3000
+    with g.ParticleFilter(n) as a, g.ParticleFilter(n) as b:
+        want = [a.step(scans[f], f) for f in range(1, 41)]
+        got, pending = [], []
+        for f in range(1, 41):
+            pending.append(b.submit(scans[f], f))
+            if len(pending) == g.RING_DEPTH:
+                with pytest.raises(g.PfslamError, match="ring full"):
+                    b.submit(scans[f], f)
+                got.append(b.wait(pending.pop(0)))
+        while pending:
+            got.append(b.wait(pending.pop(0)))
+        with pytest.raises(g.PfslamError):
+            b.wait(12345)
+        for f, (x, y) in enumerate(zip(want, got), 1):
+            assert np.array_equal(bits(list(x.pose)), bits(list(y.pose))), "frame %d" % f
+            assert (x.fit_min, x.fit_max, x.best_index, x.resampled, x.n_free_cells, x.n_wall_cells) == \
+                   (y.fit_min, y.fit_max, y.best_index, y.resampled, y.n_free_cells, y.n_wall_cells), "frame %d" % f
+        assert np.array_equal(a.get_grid(), b.get_grid())
+        # and the blocking call still works after the ring has been used
+        ra, rb = a.step(scans[41], 41), b.step(scans[41], 41)
+        assert np.array_equal(bits(list(ra.pose)), bits(list(rb.pose)))
