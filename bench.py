@@ -265,6 +265,23 @@ def reference_gpu_leg(scans, order, n_warm, n_timed, kd):
     scene = os.path.join(ROOT, "oracle", "_ref", "map_settings.txt")
     if not (os.path.exists(so) and os.path.exists(scene)):
         return {"unavailable": "oracle/_ref/libref_t3_65536.so not built (needs /root/reference at build time)"}
+    # the reference prints to stdout (scene parser, per-100-frame timers); this process's stdout carries the one JSON
+    # line, so the C-level stdout is pointed at stderr for the duration of the leg
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _reference_gpu_leg(so, scene, scans, order, n_warm, n_timed, kd)
+    finally:
+        try:
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+
+
+def _reference_gpu_leg(so, scene, scans, order, n_warm, n_timed, kd):
     fp = C.POINTER(C.c_float)
     lib = C.CDLL(so)
     lib.t3_init.argtypes = [C.c_char_p]

@@ -46,6 +46,7 @@ constexpr float kGuardT = 64.0f;            // units of 2^-16 cell; band test = 
 constexpr double kRotBudgetUnits = 26.0;    // share of the rounding of rot = angle + theta in the 64-unit guard band
 constexpr int kBoxMargin = 2;               // cells added around the conservative hit box
 constexpr int kWindowCostBeams = 8;         // fixed cost of a window (TMA wait, re-layout, two barriers) in beam units
+constexpr int kShareFactor = 1;             // k_score_tiled: shares per block (first static, rest claimed on completion); 2 measured no better than 1: the tail is not block imbalance
 
 // stage table of k_score_staged (pf_score_staged.cuh), built by k_tile_prep's last warp
 constexpr int kStageWindows = 5;            // windows resident per stage (5 x 34.9 KB of shared memory)
@@ -79,6 +80,7 @@ struct TiledWork {
     int4 stage[kMaxStages];                    // {kind, first window / list index, beams, units of the line before it (per group)}
     int sfirst[kMaxStages + 1];                // first block of stage s; sfirst[n_stages] = blocks
     int n_stages, u_total, aligned;            // aligned: the slices are stage-aligned (enough blocks), else equal cuts
+    int share_next;                            // k_score_tiled: next unclaimed share beyond the first wave (reset per frame)
 };
 
 __global__ void k_bounds_reset(TiledWork *__restrict__ tw)
@@ -402,7 +404,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
         tw->stat_wide = nf; tw->stat_slow = ns;
         // consumed: reset the cloud bounds for the next frame's k_motion, and the per-frame counters
         for (int q = 0; q < 3; q++) { tw->bounds[2 * q] = 0x7fffffff; tw->bounds[2 * q + 1] = (int)0x80000000; }
-        tw->wide_run = 0; tw->slow_run = 0; tw->done = 0;
+        tw->wide_run = 0; tw->slow_run = 0; tw->done = 0; tw->share_next = 0;
     }
 }
 
@@ -516,39 +518,12 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
 #pragma unroll
     for (int k = 0; k < PPT; k++) sm.acc[tid + k * THREADS] = 0;
     __syncthreads();
-    if (tid == 0) {
-        // this block's share [item0, item1): items whose first work unit falls into its slice of the
-        // (groups x frame work) line
-        int i0 = 0, i1 = 0;
-        const int bt = n_chunks > 0 ? sm.cum[n_chunks] : 0;
-        if (bt > 0) {
-            const int n_groups = (n + kTiledGroup - 1) / kTiledGroup;
-            const long long total = (long long)n_groups * bt;
-            const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
-            for (int e = 0; e < 2; e++) {
-                const long long u = e ? hi : lo;
-                const int gq = (int)(u / bt), rem = (int)(u - (long long)gq * bt);
-                int a = 0, b = n_chunks;                         // first c with cum[c] >= rem
-                while (a < b) { const int mid = (a + b) >> 1; if (sm.cum[mid] < rem) a = mid + 1; else b = mid; }
-                (e ? i1 : i0) = gq * n_chunks + a;
-            }
-        }
-        sm.item0 = i0; sm.item1 = i1;
-    }
-    __syncthreads();
-    const int item0 = sm.item0, item1 = sm.item1;
-    if (item0 >= item1) return;
-    // prologue: the first window of this block in flight, and its beam constants
-    if (tid == 0) {
-        mbar_expect_tx(&sm.bar, kTileBytes);
-        const int4 w0 = sm.win[item0 % n_chunks];
-        tma_load_2d(sm.stage, &tmap, w0.y, w0.x, &sm.bar);
-    }
-    if (tid < kChunkBeams) {
-        const int4 w0 = sm.win[item0 % n_chunks];
-        sm.cst[0][tid] = tid < w0.z ? tw->tconst[w0.w * kChunkBeams + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
+    // The frame's work line is cut into kShareFactor x gridDim.x equal shares.  Every block starts on share blockIdx.x;
+    // a block that finishes claims the next unclaimed one (tw->share_next), so the blocks whose windows turned out
+    // cheap (few bank conflicts, few uncertain pairs) take work off the tail instead of idling.
+    const int n_shares = kShareFactor * (int)gridDim.x;
+    int share = blockIdx.x;
+    unsigned tma_n = 0;                        // TMA loads this block has waited for so far (mbarrier phase)
     const float c0x = __fdiv_rn(__fmul_rn(0.5f, g.scale_x), g.res_x);
     const float c0y = __fdiv_rn(__fmul_rn(0.5f, g.scale_y), g.res_y);
     const float unit = (float)(1 << kFracT);
@@ -591,6 +566,39 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         if (tid == 0) { if (sm.npairs) atomicAdd(&counters[2], sm.npairs); sm.qn = 0; sm.npairs = 0; }
     };
 
+    for (;;) {
+    if (tid == 0) {
+        // share [item0, item1): items whose first work unit falls into its slice of the (groups x frame work) line
+        int i0 = 0, i1 = 0;
+        const int bt = n_chunks > 0 ? sm.cum[n_chunks] : 0;
+        if (bt > 0) {
+            const int n_groups = (n + kTiledGroup - 1) / kTiledGroup;
+            const long long total = (long long)n_groups * bt;
+            const long long lo = total * share / n_shares, hi = total * (share + 1) / n_shares;
+            for (int e = 0; e < 2; e++) {
+                const long long u = e ? hi : lo;
+                const int gq = (int)(u / bt), rem = (int)(u - (long long)gq * bt);
+                int a = 0, b = n_chunks;                         // first c with cum[c] >= rem
+                while (a < b) { const int mid = (a + b) >> 1; if (sm.cum[mid] < rem) a = mid + 1; else b = mid; }
+                (e ? i1 : i0) = gq * n_chunks + a;
+            }
+        }
+        sm.item0 = i0; sm.item1 = i1;
+    }
+    __syncthreads();
+    const int item0 = sm.item0, item1 = sm.item1;
+    if (item0 < item1) {
+    // prologue: the first window of this share in flight, and its beam constants
+    if (tid == 0) {
+        mbar_expect_tx(&sm.bar, kTileBytes);
+        const int4 w0 = sm.win[item0 % n_chunks];
+        tma_load_2d(sm.stage, &tmap, w0.y, w0.x, &sm.bar);
+    }
+    if (tid < kChunkBeams) {
+        const int4 w0 = sm.win[item0 % n_chunks];
+        sm.cst[0][tid] = tid < w0.z ? tw->tconst[w0.w * kChunkBeams + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    grp = -1;
     for (int it = item0; it < item1; it++) {
         const int li = it - item0, s = li & 1;
         const int gi = it / n_chunks, ci = it - gi * n_chunks;
@@ -624,7 +632,7 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         for (int k = 0; k < PPT; k++)
             P[k] = make_float2(__fmaf_rn(__fmaf_rn(px[k], irx, offx), unit, mconst),
                                __fmaf_rn(__fmaf_rn(py[k], iry, offy), unit, mconst));
-        mbar_wait(&sm.bar, li & 1);            // window landed in `stage`
+        mbar_wait(&sm.bar, (tma_n + (unsigned)li) & 1u);   // window landed in `stage`
         __syncthreads();                       // every warp has left the previous window's gather loop
         if (tid < 2 * kTileX) {   // re-lay the dense 128x128 box out: pitch 272, 16-byte group q of a row at byte 17 q
             const int r = tid >> 1, h = tid & 1;
@@ -714,6 +722,16 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
         }
     }
     flush();
+    tma_n += (unsigned)(item1 - item0);
+    }
+    // the next unclaimed share, if any
+    __syncthreads();
+    if (tid == 0) sm.item0 = (int)gridDim.x + atomicAdd(const_cast<int *>(&tw->share_next), 1);
+    __syncthreads();
+    share = sm.item0;
+    __syncthreads();                           // before thread 0 writes the item range of the next share
+    if (share >= n_shares) break;
+    }
 }
 
 // fit[p] = sum of n_rows partial rows; per-256-particle min / max-key partials
