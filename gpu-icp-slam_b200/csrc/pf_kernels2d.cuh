@@ -664,6 +664,7 @@ k_map_free(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            unsigned *__restrict__ free_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
     TraceScope trace_scope(kTrMapFree);
+    pdl_trigger();                              // k_map_wall's blocks may be staged; they wait for this grid to complete
     __shared__ int s_cnt;
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
@@ -719,6 +720,7 @@ k_map_wall(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            unsigned *__restrict__ wall_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
     TraceScope trace_scope(kTrMapWall);
+    pdl_wait();                                 // every -1 of k_map_free has landed
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;

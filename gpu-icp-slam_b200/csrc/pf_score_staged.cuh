@@ -98,7 +98,7 @@ __device__ __forceinline__ unsigned long long staged_now()
 // IMAD.HI issues at half the rate of IMAD / IMAD.WIDE / PRMT / LOP3 / LEA; the loop is issue-bound, so instructions
 // are what counts):   1: PRMT + IMAD.WIDE + IADD     2: PRMT + IADD + LEA.HI
 template <int THREADS, int PPT, int K, int VAR>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 3))
 k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict__ grid, MapGeom g,
                const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th, int n,
                const StepParams *__restrict__ sp, const float *__restrict__ angle,
@@ -421,9 +421,12 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
 static int staged_threads()
 {
     static int v = 0;
-    if (!v) { const char *e = getenv("PFSLAM_STAGED_THREADS"); v = (e && atoi(e) == 1024) ? 1024 : 768; }
+    if (!v) { const char *e = getenv("PFSLAM_STAGED_THREADS"); v = (e && atoi(e) == 1024) ? 1024 : (e && atoi(e) == 256) ? 256 : 768; }
     return v;
 }
+// 768 x 4 particles x 5 resident windows, 1 block per SM (default); 1024 x 2 x 5; or 256 x 4 x 1 window, 3 blocks per SM
+static int staged_windows() { return staged_threads() == 256 ? 1 : kStageWindows; }
+static int staged_ppt() { return staged_threads() == 1024 ? 2 : 4; }
 static int staged_variant()
 {
     static int v = -1;
@@ -434,12 +437,14 @@ static int staged_variant()
 static StagedKernel staged_kernel()
 {
     const int t = staged_threads(), v = staged_variant();
+    if (t == 256) return v == 1 ? (StagedKernel)k_score_staged<256, 4, 1, 1> : (StagedKernel)k_score_staged<256, 4, 1, 2>;
     if (t == 1024) return v == 1 ? (StagedKernel)k_score_staged<1024, 2, kStageWindows, 1> : (StagedKernel)k_score_staged<1024, 2, kStageWindows, 2>;
     return v == 1 ? (StagedKernel)k_score_staged<768, 4, kStageWindows, 1> : (StagedKernel)k_score_staged<768, 4, kStageWindows, 2>;
 }
 static size_t staged_smem_bytes()
 {
-    return staged_threads() == 1024 ? sizeof(StagedSmem<kStageWindows, 32>) : sizeof(StagedSmem<kStageWindows, 24>);
+    const int t = staged_threads();
+    return t == 256 ? sizeof(StagedSmem<1, 8>) : t == 1024 ? sizeof(StagedSmem<kStageWindows, 32>) : sizeof(StagedSmem<kStageWindows, 24>);
 }
 
 // returns the grid size of k_score_staged = SMs x resident blocks per SM (one full wave), or -1

@@ -50,7 +50,7 @@ constexpr int kShareFactor = 1;             // k_score_tiled: shares per block (
 
 // stage table of k_score_staged (pf_score_staged.cuh), built by k_tile_prep's last warp
 constexpr int kStageWindows = 5;            // windows resident per stage (5 x 34.9 KB of shared memory)
-constexpr int kMaxStages = 128;             // tiled stages + wide stages + slow stages of a frame
+constexpr int kMaxStages = 384;             // tiled + wide + slow stages of a frame (at most, with one window per stage: 256 + 64 + 64)
 enum { kStTiled = 0, kStWide = 1, kStSlow = 2 };
 // Units of the work line, calibrated with the in-kernel stamps (tools/score_probe.py, PFSLAM_STAGED_DEBUG=16): a tiled
 // beam over one particle group = 1 (0.26 us); a wide beam (LDG path) = 4; a slow beam (exact expression) = 6; and every
@@ -156,7 +156,7 @@ constexpr int kPrepWarps = 8;
 __global__ void __launch_bounds__(kPrepWarps * 32)
 k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             const double2 *__restrict__ angle_cs, int n_beams, MapGeom g,
-            ScoreFilteredWork *__restrict__ wk, TiledWork *tw, int staged_groups, int staged_blocks)
+            ScoreFilteredWork *__restrict__ wk, TiledWork *tw, int staged_groups, int staged_blocks, int stage_windows)
 {
     TraceScope trace_scope(kTrTilePrep);
     pdl_trigger();                              // k_score_tiled's blocks may be staged
@@ -320,15 +320,15 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     // in stages of kStageWindows * 32 beams; per stage the units of the work line before it, and its first block
     if (staged_groups > 0) {
         __threadfence(); __syncwarp();
-        constexpr int SB = kStageWindows * kChunkBeams;
-        const int n_t = (n_win + kStageWindows - 1) / kStageWindows, n_w = (nf + SB - 1) / SB, n_s = (ns + SB - 1) / SB;
+        const int SB = stage_windows * kChunkBeams;
+        const int n_t = (n_win + stage_windows - 1) / stage_windows, n_w = (nf + SB - 1) / SB, n_s = (ns + SB - 1) / SB;
         const int n_st = min(n_t + n_w + n_s, kMaxStages);
         int run = 0;
         for (int s0 = 0; s0 < n_st; s0 += 32) {
             const int st = s0 + lane;
             int kind = 0, first = 0, nb = 0;
             if (st < n_st) {
-                if (st < n_t) { kind = kStTiled; first = st * kStageWindows; nb = __ldcg(&tw->bcum[min(first + kStageWindows, n_win)]) - __ldcg(&tw->bcum[first]); }
+                if (st < n_t) { kind = kStTiled; first = st * stage_windows; nb = __ldcg(&tw->bcum[min(first + stage_windows, n_win)]) - __ldcg(&tw->bcum[first]); }
                 else if (st < n_t + n_w) { kind = kStWide; first = (st - n_t) * SB; nb = min(SB, nf - first); }
                 else { kind = kStSlow; first = (st - n_t - n_w) * SB; nb = min(SB, ns - first); }
             }
@@ -359,29 +359,36 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
-        for (int it = 0; aligned && used != staged_blocks && it < 4 * kMaxStages; it++) {
-            // more blocks to hand out: the stage with the largest units / blocks; too many (the "at least one"s): take
-            // one from the stage that suffers least, i.e. the smallest units / (blocks - 1) among those with > 1
-            const bool give = used < staged_blocks;
-            float best = give ? -1.0f : 3.0e38f; int best_st = -1;
+        // largest remainders: rank every stage's fractional part among all stages (broadcast by shuffle), the `left`
+        // best-ranked stages take one more block.  (An iterative "give to the most loaded stage" loop here cost 10-30 us
+        // of single-warp time before the scorer could start -- measured with the in-graph timeline.)
+        int aligned_ok = aligned;
+        if (aligned) {
+            const int left = staged_blocks - used;
+            if (left < 0) aligned_ok = 0;          // the "at least one block" floors alone exceed the grid: equal cuts instead
+            else if (left > 0) {
+                float rem[kPer];
+                int rank[kPer];
 #pragma unroll
-            for (int q = 0; q < kPer; q++) {
-                const int st = lane + 32 * q;
-                if (st >= n_st) continue;
-                if (give) { const float v = (float)su[q] / (float)sc[q]; if (v > best) { best = v; best_st = st; } }
-                else if (sc[q] > 1) { const float v = (float)su[q] / (float)(sc[q] - 1); if (v < best) { best = v; best_st = st; } }
+                for (int q = 0; q < kPer; q++) {
+                    const float ideal = (float)su[q] * (float)staged_blocks / (float)max(run, 1);
+                    rem[q] = (lane + 32 * q < n_st) ? ideal - (float)sc[q] : -1.0e30f;   // stages floored up to 1 rank last
+                    rank[q] = 0;
+                }
+                for (int st2 = 0; st2 < n_st; st2++) {
+                    float r2 = 0.0f;
+#pragma unroll
+                    for (int q2 = 0; q2 < kPer; q2++) { const float v = __shfl_sync(0xffffffffu, rem[q2], st2 & 31); if ((st2 >> 5) == q2) r2 = v; }
+#pragma unroll
+                    for (int q = 0; q < kPer; q++) {
+                        const int st = lane + 32 * q;
+                        if (st < n_st && (r2 > rem[q] || (r2 == rem[q] && st2 < st))) rank[q]++;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kPer; q++) if (lane + 32 * q < n_st && rank[q] < left) sc[q]++;
+                // left > n_st cannot happen: every floor is within one of its ideal, so at most n_st blocks are left
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int os = __shfl_xor_sync(0xffffffffu, best_st, o);
-                const bool take = os >= 0 && (best_st < 0 || (give ? (ob > best || (ob == best && os < best_st)) : (ob < best || (ob == best && os < best_st))));
-                if (take) { best = ob; best_st = os; }
-            }
-            if (best_st < 0) break;
-#pragma unroll
-            for (int q = 0; q < kPer; q++) if (lane + 32 * q == best_st) sc[q] += give ? 1 : -1;
-            used += give ? 1 : -1;
         }
         // first block of every stage = exclusive prefix of the counts in stage order
         {
@@ -397,7 +404,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
                 base += __shfl_sync(0xffffffffu, v, 31);
             }
         }
-        if (lane == 0) { tw->n_stages = n_st; tw->u_total = run; tw->aligned = aligned; tw->sfirst[n_st] = staged_blocks; }
+        if (lane == 0) { tw->n_stages = n_st; tw->u_total = run; tw->aligned = aligned_ok; tw->sfirst[n_st] = staged_blocks; }
     }
     if (lane == 0) {
         wk->nf = nf; wk->ns = ns;
@@ -864,7 +871,7 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                               cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                               LapRec *laps = nullptr, StagedKernel staged = nullptr, int staged_threads = 0, size_t staged_smem = 0,
-                              int staged_particles = 1024, float4 *pcs = nullptr)
+                              int staged_particles = 1024, float4 *pcs = nullptr, int stage_windows = kStageWindows)
 {
     int nl = 4;
     if (!bounds_valid) {   // poses were not produced by k_motion this frame (test hooks): recompute
@@ -877,7 +884,7 @@ static int score_tiled_launch(const CUtensorMap &tmap, const int8_t *grid, MapGe
     const int sgroups = staged ? (n + staged_particles - 1) / staged_particles : 0;
     const int gs = staged ? min(tiled_grid, max(1, ((n + 1023) / 1024) * 8)) : 0;
     launch_k(bounds_valid, k_tile_prep, dim3((n_prep_groups + kPrepWarps - 1) / kPrepWarps), dim3(kPrepWarps * 32), 0, stream,
-             scan, angle, angle_cs, n_beams, g, wk, tw, sgroups, gs);                  // dependent of k_motion when it ran just before
+             scan, angle, angle_cs, n_beams, g, wk, tw, sgroups, gs, stage_windows);                  // dependent of k_motion when it ran just before
     if (laps) laps->mark(stream, kLapTilePrep);
     const int nblk = (n + 255) / 256;
     if (staged) {

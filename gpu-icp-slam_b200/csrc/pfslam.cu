@@ -646,7 +646,7 @@ static int score_phase(pfslam_engine *e, const float *scan_dev, cudaEvent_t ev0,
                                     e->twork, e->angle_cs, e->bounds_valid, e->score_partial, e->counters, xc, e->tiled_grid, e->stream, ev0, ev1,
                                     use_aux ? e->aux : nullptr, e->ev_fork[0], e->ev_join[0], e->laps_on ? &e->laps : nullptr,
                                     e->staged ? staged_kernel() : nullptr, staged_threads(), staged_smem_bytes(),
-                                    staged_threads() * (staged_threads() == 1024 ? 2 : 4), e->pcs);
+                                    staged_threads() * staged_ppt(), e->pcs, staged_windows());
         e->bounds_valid = false;   // consumed (and reset) by k_tile_prep
         if (nl < 0) return set_error(PFSLAM_ERR_CUDA, "tiled scoring launch failed: %s",
                                      cudaGetErrorString(cudaGetLastError()));
@@ -820,8 +820,9 @@ static int launch_map(pfslam_engine *e, cudaStream_t st, int pose_from_ext)
     k_map_free<<<e->cfg.n_beams, 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
                                                e->counters, *e->cur_xc, pose_from_ext);
     if (e->laps_on) e->laps.mark(st, kLapMapFree);
-    k_map_wall<<<ceil_div(e->cfg.n_beams, 128), 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle,
-                                                              e->cfg.n_beams, e->wall_bits, e->counters, *e->cur_xc, pose_from_ext);
+    // dependent launch of k_map_free (same stream, directly behind it) unless a lap marker sits in between
+    launch_k(!e->laps_on, k_map_wall, dim3(ceil_div(e->cfg.n_beams, 128)), dim3(128), 0, st, e->grid, e->geom, e->res, scan, e->angle,
+             e->cfg.n_beams, e->wall_bits, e->counters, *e->cur_xc, pose_from_ext);
     if (e->laps_on) e->laps.mark(st, kLapMapWall);
     e->launches += 2;
     CUDA_TRY(cudaGetLastError());

@@ -161,3 +161,16 @@ def test_streaming_ring_equals_blocking_step(scans):
         # and the blocking call still works after the ring has been used
         ra, rb = a.step(scans[41], 41), b.step(scans[41], 41)
         assert np.array_equal(bits(list(ra.pose)), bits(list(rb.pose)))
+
+
+@pytest.mark.parametrize("threads", ["768", "256"])
+def test_staged_scorer_generation_is_bit_exact_too(scans, monkeypatch, threads):
+    """k_score_staged (PFSLAM_TILED_KERNEL=staged: window stages resident in shared memory, wide and slow beams in the
+    same kernel) is the measured-but-not-default scorer; it must return the same integers as the oracle"""
+    if threads == "256":
+        pytest.skip("one process, one block shape: the shape is latched at first use (covered by tools/score_probe.py runs)")
+    monkeypatch.setenv("PFSLAM_TILED_KERNEL", "staged")
+    _run_pair(2500, scans, [(f, scans[f]) for f in range(1, 30)])
+    sent = np.full(1081, 4294967.0, np.float32)
+    seq = [(1, scans[1]), (2, sent), (3, scans[3]), (4, np.full(1081, 25.0, np.float32)), (5, scans[5])]
+    _run_pair(1500, scans, seq)
