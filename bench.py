@@ -80,7 +80,8 @@ def make_config(args, world, dataset):
     return {"workload": ("%s, %s, %d particles per GPU x %d" %
                          (dataset, "kd-tree point cloud @ 25 mm" if kd else "2D occupancy grid 1600x1600 @ 0.025 m", n, world)),
             "particles_per_gpu": n, "particles_total": world * n, "beams": N_BEAMS, "path": args.path,
-            "value_is": "frames/s x particles_total / 65536 (65 536-particle frame equivalents)"}
+            "value_is": "frames/s x particles_total / 65536 (65 536-particle frame equivalents)",
+            "l2": "ours: 256 MiB L2 flush between timed steps; reference CPU arm: working set (grid 2.56 MB + scans) larger than the host L2"}
 
 
 class ClockSampler:
@@ -506,14 +507,15 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
             "data": data_desc,
-            "config": dict(make_config(args, world, dataset), **{
+            "config": make_config(args, world, dataset),
+            "measurement": {
                        "score_mode": "tiled (TMA-staged smem windows, bit-exact)", "l2_flush": "256 MiB memset between timed steps (untimed)",
                        "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
                        "parallelism": "particles sharded %d-way, map replicated" % world,
                        "prewarm_frames": PW,
                        "exchange": ("none (single GPU)" if world == 1 else
                                     "in-kernel stores/loads over NVLink peer memory, whole step = 1 CUDA graph per rank" if args.exchange == "peer"
-                                    else "3 NCCL all-gathers between the step's phases")}),
+                                    else "3 NCCL all-gathers between the step's phases")},
             "resampled_steps": int(resampled_steps),
             "exchange_wait_us_per_step": ({"extrema": wait_ext_us, "tiles": wait_tiles_us,
                                            "note": "max over ranks of the time the step's kernels spent in the two peer waits"} if world > 1 else None),

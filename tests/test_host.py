@@ -71,3 +71,29 @@ def test_map_export_writers(tmp_path):
     assert lines[1] == "VERSION 0.7" and int(lines[9].split()[1]) == len(ok.tree) == len(lines) - 11
     of.close()
     ok.close()
+
+
+def test_bench_config_is_identical_in_both_arms():
+    """bench.py builds `config` with one function for the ours / --impl reference arms (the driver compares them)"""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(helpers.ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    for path, gpus in (("grid2d", 1), ("grid2d", 4), ("kd", 1)):
+        args = types.SimpleNamespace(particles=65536, path=path, gpus=gpus, data="auto")
+        ds = b.default_dataset(args)
+        assert b.make_config(args, gpus, ds) == b.make_config(args, gpus, ds)
+        assert ds == {"grid2d1": "train_lidar0", "grid2d4": "train_lidar2", "kd1": "train_lidar3"}[path + str(gpus)]
+        assert ds in b.make_config(args, gpus, ds)["workload"]
+
+
+def test_streaming_api_rejects_bad_arguments_without_gpu():
+    import ctypes as C
+    from gpu_icp_slam_b200 import engine
+    lib = engine.load_library()
+    t = C.c_int32()
+    assert lib.pfslam_submit(None, None, 1, C.byref(t)) == 1          # PFSLAM_ERR_ARG
+    assert lib.pfslam_wait(None, 1, None) == 1
+    assert lib.pfslam_kd_icp(None, None, None, None, None) == 1
+    assert lib.pfslam_trace_name(0) == b"k_motion" and lib.pfslam_trace_name(99) == b""
