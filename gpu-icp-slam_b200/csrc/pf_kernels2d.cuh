@@ -17,6 +17,10 @@ namespace pf {
 // has executed pdl_trigger(); it must execute pdl_wait() before touching anything the earlier kernel
 // wrote (the wait returns when that grid has completed and flushed).  Both are no-ops in a normal launch.
 // Used on the step's critical-path edges to hide launch latency (PFSLAM_PDL=0 turns it off).
+// release / acquire fence at GPU scope for the "last block finishes the job" hand-overs (stores -> fence -> counter
+// atomic | counter atomic -> fence -> loads).  __threadfence() is the sequentially consistent fence (MEMBAR.SC),
+// which these do not need.
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -42,7 +46,8 @@ inline cudaError_t launch_k(bool dependent, void (*kern)(KArgs...), dim3 grid, d
 // In-graph timeline (pfslam_debug_trace): when on, thread 0 of every block folds %globaltimer into its kernel's
 // [first entry, last exit] pair -- the only way to see where the kernels of the captured step really run (programmatic
 // dependent launches and graph branches overlap them; events cannot be recorded inside a graph replay).
-enum { kTrMotion = 0, kTrTilePrep, kTrScore, kTrScoreFast, kTrCombine, kTrWeights, kTrResample, kTrMapFree, kTrMapWall, kTrPublish, kTrCount };
+enum { kTrMotion = 0, kTrTilePrep, kTrScore, kTrScoreFast, kTrCombine, kTrWeights, kTrResample, kTrMapFree, kTrMapWall, kTrPublish,
+       kTrMark0, kTrMark1, kTrMark2, kTrMark3, kTrMark4, kTrMark5, kTrCount };   // marks: [first, last] block to reach a point
 __device__ int g_trace_on = 0;
 __device__ unsigned long long g_trace[2 * 16];
 struct TraceScope {
@@ -64,6 +69,19 @@ struct TraceScope {
         }
     }
 };
+
+// diagnostic mark inside a kernel: block-wide (every thread calls it); [first block, last block] to get there
+__device__ __forceinline__ void trace_mark(int id)
+{
+    if (!g_trace_on) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(&g_trace[2 * id], t);
+        atomicMax(&g_trace[2 * id + 1], t);
+    }
+}
 
 // host side: per-kernel lap events of the serialised profiling step (pfslam_profile_laps)
 enum { kLapStart = -1, kLapMotion = 0, kLapTilePrep, kLapScoreTiled, kLapScoreFast, kLapCombine, kLapWeights,
@@ -375,6 +393,28 @@ __device__ __forceinline__ float tile_scan4(const float e[4], float lm[4], float
     return total;
 }
 
+// Sequential fp32 sum of v[0..n) in index order (the arithmetic contract's global tile order), optionally leaving
+// the inclusive prefix in place.  Loads are batched 16 ahead of the dependent adds, so the chain costs one FADD
+// latency per tile instead of a shared-memory round trip per tile (512 tiles on 8 GPUs: ~9 us -> ~1.5 us).
+__device__ __forceinline__ float chain_sum(float *v, int n, bool keep_prefix)
+{
+    float p = 0.0f;
+    int t = 0;
+    for (; t + 16 <= n; t += 16) {
+        float r[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = v[t + k];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { p = __fadd_rn(p, r[k]); r[k] = p; }
+        if (keep_prefix) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[t + k] = r[k];
+        }
+    }
+    for (; t < n; t++) { p = __fadd_rn(p, v[t]); if (keep_prefix) v[t] = p; }
+    return p;
+}
+
 // weights + tile scans.  kernel.cu:287-294 kernUpdateWeights: w = w*((float)fit - min)*c with
 // c = 1/(float)(max-min) when max > min (kernel.cu:329-331); SURVEY Q1: only the first
 // ceil(N/2) particles' new weights persist (kernel.cu:337).  Then the per-tile scans that feed
@@ -391,7 +431,6 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
     TraceScope trace_scope(kTrWeights);
     __shared__ float s_wtot[8], s_wmax[8];
     __shared__ int s_last;
-    pdl_trigger();                              // k_resample's blocks may be staged
     pdl_wait();                                 // scores and extrema of k_score_combine_rows
     const int seq = sp->seq;
     if (xc.parity_mask) {
@@ -424,8 +463,12 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         e[k] = we;
         q[k] = __fmul_rn(we, we);
     }
+    trace_mark(kTrMark3);                       // extrema and weights in registers
     float t2 = tile_scan4(q, lm2, s_wtot, s_wmax);
     float t1 = tile_scan4(e, lm, s_wtot, s_wmax);
+    trace_mark(kTrMark4);                       // tile scans done
+    pdl_trigger();                              // k_resample's blocks may be staged now (not earlier: they would sit on
+                                                // registers the map update's blocks need while this kernel works)
     if (!xc.parity_mask) {
         float *lm_out = tiles_local + xc.lm_off;
 #pragma unroll
@@ -444,11 +487,12 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         __syncthreads();          // thread 0's system fence below then covers the whole block's stores
     }
     if (threadIdx.x == 0) {
-        if (xc.parity_mask) __threadfence_system(); else __threadfence();
+        if (xc.parity_mask) __threadfence_system(); else fence_gpu();
         s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
+    trace_mark(kTrMark5);                       // the last block knows it is the last
     // The last block to finish also does k_prefix's job when asked to (global tile prefix in tile order,
     // Neff, resample decision, robotPos).  Sharded over peer memory it first raises this rank's tile
     // flags, then waits for everybody's: one spinning block, and no separate kernel on the critical path.
@@ -465,7 +509,7 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         }
         __syncthreads();
     } else {
-        __threadfence();
+        fence_gpu();
     }
     __shared__ float s_t[2 * kFusedPrefixMaxTiles];
     const int nt = xc.n_ranks * n_tiles;
@@ -482,15 +526,8 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
     // the two sequential chains (sum of w in global tile order = the CDF's tile prefix, sum of w^2) run in two
     // warps side by side, in place in shared memory; the prefix goes out to global memory in parallel afterwards
     __shared__ float s_tot[2];
-    if (threadIdx.x == 0) {
-        float p = 0.0f;
-        for (int t = 0; t < nt; t++) { p = __fadd_rn(p, s_t[t]); s_t[t] = p; }
-        s_tot[0] = p;
-    } else if (threadIdx.x == 32) {
-        float p2 = 0.0f;
-        for (int t = 0; t < nt; t++) p2 = __fadd_rn(p2, s_t[nt + t]);
-        s_tot[1] = p2;
-    }
+    if (threadIdx.x == 0) s_tot[0] = chain_sum(s_t, nt, true);
+    else if (threadIdx.x == 32) s_tot[1] = chain_sum(s_t + nt, nt, false);
     __syncthreads();
     for (int t = threadIdx.x; t <= nt; t += blockDim.x) prefix[t] = t ? s_t[t - 1] : 0.0f;
     if (threadIdx.x == 0) {
@@ -530,15 +567,8 @@ k_prefix(const Xchg xc, const StepParams *__restrict__ sp, int n_tiles_local, in
     }
     __syncthreads();
     __shared__ float s_tot[2];
-    if (threadIdx.x == 0) {
-        float p = 0.0f;
-        for (int t = 0; t < nt; t++) { p = __fadd_rn(p, s_t[t]); s_t[t] = p; }
-        s_tot[0] = p;
-    } else if (threadIdx.x == 32) {
-        float p2 = 0.0f;
-        for (int t = 0; t < nt; t++) p2 = __fadd_rn(p2, s_t[nt + t]);
-        s_tot[1] = p2;
-    }
+    if (threadIdx.x == 0) s_tot[0] = chain_sum(s_t, nt, true);
+    else if (threadIdx.x == 32) s_tot[1] = chain_sum(s_t + nt, nt, false);
     __syncthreads();
     for (int t = threadIdx.x; t <= nt; t += blockDim.x) prefix[t] = t ? s_t[t - 1] : 0.0f;
     if (threadIdx.x == 0) {
@@ -601,6 +631,202 @@ k_resample(const Xchg xc, FrameResult *res, const float *__restrict__ prefix,
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_weights_scan + the prefix step + k_resample as ONE launch with one grid-wide barrier in the middle: block t owns
+// tile t (1024 particles) in both halves.  After the barrier EVERY block sums the tile totals itself (the same
+// sequential chain, so the same bits), keeps the prefix in shared memory and resamples its own tile -- no "last
+// block" election, no prefix round trip through global memory, no dependent kernel launch on the step's critical
+// path.  The barrier needs all n_tiles blocks resident at once; the host uses this kernel only while n_tiles is a
+// fraction of what the device holds (otherwise the three-kernel sequence), and the spin is bounded like every
+// other wait of the step.
+//   single GPU : barrier = a monotone arrival counter (64-bit, never reset: a block's target is the next multiple
+//                of the grid size above its own ticket)
+//   peer memory: the last arrival raises this rank's tile flags; the barrier IS the wait for every rank's flags
+//                (this rank's own included), so the local barrier and the exchange wait are one spin.
+__global__ void __launch_bounds__(kScanThreads)
+k_weights_resample(const Xchg xc, const StepParams *__restrict__ sp, const int *__restrict__ fit,
+                   float *__restrict__ w, int n, int gidx0, int n_sync, int n_tiles, float *tiles_local,
+                   int n_global, float *__restrict__ prefix, FrameResult *__restrict__ res,
+                   unsigned long long *__restrict__ arrivals, float *__restrict__ x, float *__restrict__ y,
+                   float *__restrict__ th)
+{
+    TraceScope trace_scope(kTrWeights);
+    __shared__ float s_wtot[8], s_wmax[8];
+    __shared__ __align__(16) float s_t[2 * kFusedPrefixMaxTiles];
+    __shared__ float s_tot[2];
+    __shared__ int s_ok;
+    pdl_wait();                                 // scores and extrema of k_score_combine_rows
+    const int seq = sp->seq, frame = sp->frame;
+    if (threadIdx.x == 0) s_ok = 1;
+    if (xc.parity_mask) {
+        if (threadIdx.x < 32) {
+            const unsigned long long t0 = xc_now_ns();
+            const bool ok = xc_wait_warp(xc, kXcExt, seq);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (!ok) res->xchg_timeout = 1;
+                res->wait_ext_ns += (int)(xc_now_ns() - t0);
+            }
+        }
+        __syncthreads();
+    }
+    int gmin, gmax, best; float pose[3];
+    reduce_extrema(xc_ext(xc, seq), xc.n_ranks, gmin, gmax, best, pose, xc.parity_mask != 0);
+    const int rng = gmax - gmin;
+    const float c = rng > 0 ? __fdiv_rn(1.0f, (float)rng) : 1.0f;
+    const float fmin = (float)gmin;
+    const int base = blockIdx.x * kTile + threadIdx.x * 4;
+    float e[4], q[4], lm[4], lm2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int i = base + k;
+        float we = 0.0f;
+        if (i < n) {
+            we = w[i];
+            if (rng > 0) we = __fmul_rn(__fmul_rn(we, __fsub_rn((float)fit[i], fmin)), c);
+            if (gidx0 + i < n_sync) w[i] = we;
+        }
+        e[k] = we;
+        q[k] = __fmul_rn(we, we);
+    }
+    float t2 = tile_scan4(q, lm2, s_wtot, s_wmax);
+    float t1 = tile_scan4(e, lm, s_wtot, s_wmax);
+    if (!xc.parity_mask) {
+        float *lm_out = tiles_local + xc.lm_off;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (base + k < n) lm_out[base + k] = lm[k];
+        if (threadIdx.x == 0) { tiles_local[xc.sum_off + blockIdx.x] = t1; tiles_local[xc.sum_off + n_tiles + blockIdx.x] = t2; }
+    } else {
+        for (int r = 0; r < xc.n_ranks; r++) {
+            float *blk = reinterpret_cast<float *>(xc.peer[r] + xc.off_tiles) +
+                         ((long long)(seq & 1) * xc.n_ranks + xc.rank) * xc.tiles_block;
+            *reinterpret_cast<float4 *>(blk + xc.lm_off + base) = make_float4(lm[0], lm[1], lm[2], lm[3]);
+            if (threadIdx.x == 0) { blk[xc.sum_off + blockIdx.x] = t1; blk[xc.sum_off + n_tiles + blockIdx.x] = t2; }
+        }
+    }
+    __syncthreads();              // thread 0's fence below then covers the whole block's stores
+    // ---- grid-wide barrier -------------------------------------------------------------------------
+    if (xc.parity_mask) {
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned long long ticket = atomicAdd(arrivals, 1ull);
+            if (ticket % gridDim.x == gridDim.x - 1) xc_signal(xc, kXcTiles, seq);
+        }
+        if (threadIdx.x < 32) {
+            const unsigned long long t0 = xc_now_ns();
+            const bool ok = xc_wait_warp(xc, kXcTiles, seq);
+            if (threadIdx.x == 0) {
+                if (!ok) s_ok = 0;
+                if (blockIdx.x == 0) res->wait_tiles_ns += (int)(xc_now_ns() - t0);
+            }
+        }
+    } else if (threadIdx.x == 0) {
+        fence_gpu();
+        const unsigned long long ticket = atomicAdd(arrivals, 1ull);
+        const unsigned long long target = (ticket / gridDim.x + 1ull) * gridDim.x;
+        const unsigned long long t0 = xc_now_ns();
+        unsigned spins = 0;
+        while (*reinterpret_cast<volatile unsigned long long *>(arrivals) < target) {
+            if ((++spins & 255u) == 0u && xc_now_ns() - t0 > 2000000000ull) { s_ok = 0; break; }
+        }
+        fence_gpu();
+    }
+    __syncthreads();
+    if (g_trace_on && threadIdx.x == 0) atomicMin(&g_trace[2 * kTrResample], xc_now_ns());
+    if (!s_ok) { if (threadIdx.x == 0) res->xchg_timeout = 1; return; }    // bounded: nothing hangs, the frame is flagged
+    pdl_trigger();                              // the step's last node may be staged
+    // ---- every block: tile totals -> prefix in shared memory, Neff, decision ----------------------------
+    const int nt = xc.n_ranks * n_tiles;
+    const float *all = xc.parity_mask ? xc_tiles(xc, seq) : tiles_local;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        const int r = t / n_tiles, tl = t - r * n_tiles;
+        const float *blk = all + (long long)r * xc.tiles_block + xc.sum_off;
+        s_t[t] = __ldcg(&blk[tl]);
+        s_t[nt + t] = __ldcg(&blk[n_tiles + tl]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_tot[0] = chain_sum(s_t, nt, true);
+    else if (threadIdx.x == 32) s_tot[1] = chain_sum(s_t + nt, nt, false);
+    __syncthreads();
+    const float sum_w = s_tot[0], sum_w2 = s_tot[1];
+    const float neff = __fdiv_rn(__fmul_rn(sum_w, sum_w), sum_w2);
+    const int resampled = ((double)neff < 0.7 * (double)n_global) ? 1 : 0;
+    if (blockIdx.x == 0) {
+        for (int t = threadIdx.x; t <= nt; t += blockDim.x) prefix[t] = t ? s_t[t - 1] : 0.0f;
+        if (threadIdx.x == 0) {
+            res->pose[0] = pose[0]; res->pose[1] = pose[1]; res->pose[2] = pose[2];
+            res->fit_min = gmin; res->fit_max = gmax; res->best_index = best;
+            res->sum_w = sum_w; res->sum_w2 = sum_w2; res->neff = neff;
+            res->resampled = resampled;
+            if (resampled) res->resample_count++;
+        }
+    }
+    if (!resampled) { if (g_trace_on && threadIdx.x == 0) atomicMax(&g_trace[2 * kTrResample + 1], xc_now_ns()); return; }
+    // ---- resample this block's tile (k_resample; s_t[t-1] = prefix[t]) -----------------------------------
+    // Four particles per thread, searched side by side with fixed trip counts (branch-free lower bounds), so the
+    // dependent probes of the four overlap instead of running one particle after the other.
+    const int n_local = n;
+    float rnd[4]; int lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = blockIdx.x * kTile + k * kScanThreads + threadIdx.x;
+        uint32_t st = pf_minstd_seed(pf_seed((int)neff, frame, gidx0 + i));
+        uint32_t u = pf_minstd_next(st) - 1u;
+        rnd[k] = __fmul_rn(__fmul_rn((float)u, 4.656612873077392578125e-10f), sum_w);
+        lo[k] = 0;
+    }
+    // tile: number of leading tiles whose inclusive prefix s_t[t] is < rnd  (== first t with prefix[t+1] >= rnd)
+    int top = 1;
+    while (top * 2 <= nt) top *= 2;
+    for (int step = top; step > 0; step >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int m = lo[k] + step;
+            const bool take = (m <= nt) & (rnd[k] > s_t[min(m, nt) - 1]);
+            lo[k] = take ? m : lo[k];
+        }
+    }
+    const float *lmp[4]; float pt[4]; int cnt[4], a[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int t = min(lo[k], nt - 1);
+        const int r = (t * kTile) / n_local;
+        lmp[k] = all + (long long)r * xc.tiles_block + xc.lm_off + (t * kTile - r * n_local);
+        pt[k] = t ? s_t[t - 1] : 0.0f;
+        cnt[k] = min(kTile, n_global - t * kTile);
+        a[k] = 0;
+    }
+    // in the tile: number of leading items with prefix + lm < rnd.  Plain loads: the barrier above ordered every
+    // block's (and, through the flags, every rank's) lm stores before them, and the last probes share a cache line.
+    // (loads are unconditional on a clamped index: a branch per probe would serialise the four particles again)
+    for (int step = kTile; step > 0; step >>= 1) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = lmp[k][min(a[k] + step, cnt[k]) - 1];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int m = a[k] + step;
+            const bool take = (m <= cnt[k]) & (rnd[k] > __fadd_rn(pt[k], v[k]));
+            a[k] = take ? m : a[k];
+        }
+    }
+    float4 got[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int src = lo[k] >= nt ? n_global - 1 : lo[k] * kTile + (a[k] < cnt[k] ? a[k] : cnt[k] - 1);
+        const int r = src / n_local, l = src - r * n_local;
+        const float *pp = xc.pose_src[r] + (long long)(seq & xc.parity_mask) * xc.snap_stride;
+        if (xc.snap_aos) got[k] = reinterpret_cast<const float4 *>(pp)[l];
+        else got[k] = make_float4(pp[l], pp[n_local + l], pp[2 * n_local + l], 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = blockIdx.x * kTile + k * kScanThreads + threadIdx.x;
+        if (i < n_local) { x[i] = got[k].x; y[i] = got[k].y; th[i] = got[k].z; w[i] = 1.0f; }
+    }
+    if (g_trace_on && threadIdx.x == 0) atomicMax(&g_trace[2 * kTrResample + 1], xc_now_ns());
+}
+
+// ---------------------------------------------------------------------------------------------
 // map update.  kernel.cu:551-555 center cell; :524-549 kernGetWalls; :190-240 traceRay;
 // :513-522 kernUpdateMap (-1 once per free cell, then +4 once per wall cell, clamp +-113).
 __device__ __forceinline__ void center_cell(const MapGeom &g, float rx, float ry, int &cx, int &cy)
@@ -630,14 +856,7 @@ __device__ __forceinline__ int8_t clamp_add(int8_t v, int d)
     return (int8_t)(t < -kClamp ? -kClamp : t > kClamp ? kClamp : t);
 }
 
-// Map update, free cells: block = one beam, threads stride over the Bresenham steps.  Step k of
-// traceRay is closed-form: x = sx+k, y = sy + ystep*m_k, m_k = max(0, ceil((k*deltay - deltax/2)/deltax)).
-// The first thread to set a cell's bit this frame applies the -1 (== the reference's bool mask).
-// Each thread issues the bit-set atomics of up to 8 steps before touching the grid so their
-// latencies overlap.
-// robotPos for the map update: the frame result (explicit-pose entry point, phase-by-phase hosts), or --
-// when the map update runs as a branch of the step graph next to the weight/resample kernels -- the
-// best particle's pose straight from the exchanged extrema (== what k_prefix writes into the result).
+// robotPos for the map update: the frame result, or the best particle's pose from the exchanged extrema (below)
 __device__ __forceinline__ void map_pose(const FrameResult *__restrict__ res, const Xchg &xc, int seq, int pose_from_ext,
                                          float pose[3])
 {
@@ -658,96 +877,170 @@ __global__ void k_xc_wait(const Xchg xc, const StepParams *__restrict__ sp, int 
     if (!ok && threadIdx.x == 0) res->xchg_timeout = 1;
 }
 
-__global__ void __launch_bounds__(128)
+// One beam's ray as traceRay sets it up (kernel.cu:190-214): endpoints swapped so that x is the major axis and
+// ascending; `ring` below is the distance from the robot's cell along the major axis (== the Chebyshev distance of
+// the visited cell, because Bresenham's minor offset never exceeds the major one).
+struct FreeRay {
+    int  sx, sy, deltax, deltay, e0, ystep;
+    bool steep, swapped, valid;
+};
+__device__ __forceinline__ FreeRay free_ray(const MapGeom &g, const float *pose, int cx, int cy, float angle, float r)
+{
+    FreeRay L;
+    float wx, wy;
+    L.valid = beam_hit(g, pose, cx, cy, angle, r, wx, wy);
+    int sx = cx, sy = cy, ex = (int)wx, ey = (int)wy;
+    L.steep = abs(ey - sy) > abs(ex - sx);
+    int t;
+    if (L.steep) { t = sx; sx = sy; sy = t; t = ex; ex = ey; ey = t; }
+    L.swapped = sx > ex;
+    if (L.swapped) { t = sx; sx = ex; ex = t; t = sy; sy = ey; ey = t; }
+    L.sx = sx; L.sy = sy;
+    L.deltax = ex - sx; L.deltay = abs(ey - sy); L.e0 = L.deltax / 2;
+    L.ystep = ey > sy ? 1 : -1;
+    return L;
+}
+// cell index of traceRay's step k (closed form, see the header comment of the map update), or -1 when the step does
+// not exist or falls outside the map
+__device__ __forceinline__ int free_ray_cell(const FreeRay &L, const MapGeom &g, int k)
+{
+    if (!L.valid || k < 0 || k >= L.deltax) return -1;
+    const int num = k * L.deltay - L.e0;
+    const int m = num > 0 ? (num + L.deltax - 1) / L.deltax : 0;
+    const int xx = L.sx + k, yy = L.sy + L.ystep * m;
+    const int id = L.steep ? yy * g.w + xx : xx * g.w + yy;
+    return (xx < g.w && yy < g.h && xx >= 0 && yy >= 0 && id < g.w * g.h) ? id : -1;
+}
+
+// Map update, free cells: block = one beam, threads stride over the Bresenham steps (closed form, so every step is
+// independent).  "-1 once per cell" (the reference's bool mask): a cell is claimed by exchanging this update's epoch
+// into a 32-bit stamp per cell; whoever reads back an older stamp applies the -1.
+//   * stamps, not a bitmap: atomics on one 32-byte sector serialise in L2 (~15 ns each, measured), and with one bit
+//     per cell a sector covers 256 cells of a row, which several hundred x-major beams cross -- the bitmap version
+//     waited 8 us for its atomics.  A stamp sector covers 8 cells; and the stamps need no clearing between frames.
+//   * adjacent beams trace the same cells out to ~230 cells from the robot: a step is skipped when the previous beam
+//     visits the same cell at the same ring (checked exactly), so the lowest beam of a run claims it -- 3x fewer
+//     atomics, none of them piled on the cells around the robot.
+// The cell's old value is loaded next to the claim (nobody else writes the cell during this kernel).
+// robotPos for the map update: the frame result (explicit-pose entry point, phase-by-phase hosts), or --
+// when the map update runs as a branch of the step graph next to the weight/resample kernels -- the
+// best particle's pose straight from the exchanged extrema (== what k_prefix writes into the result).
+constexpr int kFreeUnroll = 4;      // steps per thread in flight (4 x 128 = 512 steps per pass: one pass for rays up to 12.8 m)
+__global__ void __launch_bounds__(128, 12)
 k_map_free(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle,
-           unsigned *__restrict__ free_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
+           unsigned *__restrict__ stamps, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
     TraceScope trace_scope(kTrMapFree);
     pdl_trigger();                              // k_map_wall's blocks may be staged; they wait for this grid to complete
     __shared__ int s_cnt;
+    __shared__ FreeRay s_ray[2];
     const float *__restrict__ scan = sp->scan;
     const int j = blockIdx.x;
-    if (threadIdx.x == 0) s_cnt = 0;
+    const unsigned epoch = (unsigned)__ldcg(&counters[10]) + 1u;      // k_map_wall closes the epoch
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < 64) {                // this beam's ray and the previous beam's, one warp each
+        const int which = threadIdx.x >> 5, jj = j - which;
+        if (which == 0) s_cnt = 0;
+        FreeRay R; R.valid = false;
+        if (jj >= 0) {
+            float pose[3];
+            map_pose(res, xc, sp->seq, pose_from_ext, pose);
+            int cx, cy; center_cell(g, pose[0], pose[1], cx, cy);
+            R = free_ray(g, pose, cx, cy, angle[jj], scan[jj]);
+        }
+        s_ray[which] = R;
+    }
     __syncthreads();
-    float pose[3];
-    map_pose(res, xc, sp->seq, pose_from_ext, pose);
-    int cx, cy; center_cell(g, pose[0], pose[1], cx, cy);
-    float wx, wy;
+    const FreeRay L = s_ray[0], P = s_ray[1];
+    trace_mark(kTrMark0);                       // pose and rays known
     int mine = 0;
-    if (beam_hit(g, pose, cx, cy, angle[j], scan[j], wx, wy)) {
-        int sx = cx, sy = cy, ex = (int)wx, ey = (int)wy;
-        const bool steep = abs(ey - sy) > abs(ex - sx);
-        int t;
-        if (steep) { t = sx; sx = sy; sy = t; t = ex; ex = ey; ey = t; }
-        if (sx > ex) { t = sx; sx = ex; ex = t; t = sy; sy = ey; ey = t; }
-        const int deltax = ex - sx, deltay = abs(ey - sy), e0 = deltax / 2;
-        const int ystep = ey > sy ? 1 : -1;
-        for (int k0 = threadIdx.x; k0 < deltax; k0 += 8 * blockDim.x) {
-            int idx[8]; bool first[8];
+    if (L.valid) {
+        for (int k0 = threadIdx.x; k0 < L.deltax; k0 += kFreeUnroll * blockDim.x) {
+            int idx[kFreeUnroll]; unsigned old[kFreeUnroll]; int8_t v[kFreeUnroll];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < kFreeUnroll; u++) {
                 const int k = k0 + u * blockDim.x;
-                first[u] = false; idx[u] = 0;
-                if (k < deltax) {
-                    int num = k * deltay - e0;
-                    int m = num > 0 ? (num + deltax - 1) / deltax : 0;
-                    int xx = sx + k, yy = sy + ystep * m;
-                    int id = steep ? yy * g.w + xx : xx * g.w + yy;
-                    if (xx < g.w && yy < g.h && xx >= 0 && yy >= 0 && id < g.w * g.h) {
-                        unsigned bit = 1u << (id & 31);
-                        unsigned old = atomicOr(&free_bits[id >> 5], bit);
-                        first[u] = !(old & bit); idx[u] = id;
-                    }
+                int id = free_ray_cell(L, g, k);
+                if (id >= 0) {
+                    const int ring = L.swapped ? L.deltax - k : k;
+                    if (free_ray_cell(P, g, P.swapped ? P.deltax - ring : ring) == id) id = -1;   // the previous beam has it
+                }
+                idx[u] = id; old[u] = epoch; v[u] = 0;
+                if (id >= 0) { old[u] = atomicExch(&stamps[id], epoch); v[u] = grid[id]; }
+            }
+            if (g_trace_on && threadIdx.x == 0) {            // thread 0's atomics have returned
+                unsigned any = 0;
+#pragma unroll
+                for (int u = 0; u < kFreeUnroll; u++) any += old[u];
+                if (any != 0xFFFFFFFFu) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    atomicMin(&g_trace[2 * kTrMark1], t);
+                    atomicMax(&g_trace[2 * kTrMark1 + 1], t);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (first[u]) { grid[idx[u]] = clamp_add(grid[idx[u]], kFreeWeight); mine++; }
+            for (int u = 0; u < kFreeUnroll; u++)
+                if (old[u] != epoch) { grid[idx[u]] = clamp_add(v[u], kFreeWeight); mine++; }
         }
     }
+    trace_mark(kTrMark2);                       // cells updated
     if (mine) atomicAdd(&s_cnt, mine);
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&counters[0], s_cnt);
 }
 
-// wall cells: one thread per beam; runs after k_map_free has completed (stream order), so the +4
-// lands on top of the -1 exactly like the reference's two kernUpdateMap launches.  The last block
-// publishes the frame's cell counters.
-__global__ void __launch_bounds__(128)
+// wall cells: ONE block, threads stride over the beams; runs after k_map_free has completed, so the +4 lands on top
+// of the -1 exactly like the reference's two kernUpdateMap launches.  Only the grid update itself depends on the
+// free pass: the pose, the hit cell and the claim in the wall mask are computed while k_map_free is still running
+// (dependent launch).  Publishes the frame's cell counters.
+constexpr int kWallThreads = 1024, kWallPerThread = 2;
+__global__ void __launch_bounds__(kWallThreads)
 k_map_wall(int8_t *__restrict__ grid, MapGeom g, FrameResult *__restrict__ res,
            const StepParams *__restrict__ sp, const float *__restrict__ angle, int n_beams,
            unsigned *__restrict__ wall_bits, int *__restrict__ counters, const Xchg xc, int pose_from_ext)
 {
     TraceScope trace_scope(kTrMapWall);
-    pdl_wait();                                 // every -1 of k_map_free has landed
     const float *__restrict__ scan = sp->scan;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    float pose[3];
+    if (pose_from_ext) map_pose(res, xc, sp->seq, 1, pose);   // extrema: final before either map kernel was launched
+    else { pdl_wait(); map_pose(res, xc, sp->seq, 0, pose); }
+    int cx, cy; center_cell(g, pose[0], pose[1], cx, cy);
     int mine = 0;
-    if (j < n_beams) {
-        float pose[3];
-        map_pose(res, xc, sp->seq, pose_from_ext, pose);     // k_map_free (same stream) already waited
-        int cx, cy; center_cell(g, pose[0], pose[1], cx, cy);
-        float wx, wy;
-        if (beam_hit(g, pose, cx, cy, angle[j], scan[j], wx, wy)) {
-            if (wx >= 0.0f && wx < (float)g.w && wy >= 0.0f && wy < (float)g.h) {
-                int idx = (int)__fmaf_rn(wx, (float)g.w, wy);
-                unsigned bit = 1u << (idx & 31);
-                unsigned old = atomicOr(&wall_bits[idx >> 5], bit);
-                if (!(old & bit)) { grid[idx] = clamp_add(grid[idx], kOccupiedWeight); mine = 1; }
+    for (int j0 = 0; j0 < n_beams; j0 += kWallThreads * kWallPerThread) {      // one pass for up to 2048 beams
+        int idx[kWallPerThread]; bool first[kWallPerThread];
+#pragma unroll
+        for (int u = 0; u < kWallPerThread; u++) {
+            const int j = j0 + threadIdx.x + u * kWallThreads;
+            first[u] = false; idx[u] = 0;
+            float wx, wy;
+            if (j < n_beams && beam_hit(g, pose, cx, cy, angle[j], scan[j], wx, wy) &&
+                wx >= 0.0f && wx < (float)g.w && wy >= 0.0f && wy < (float)g.h) {
+                idx[u] = (int)__fmaf_rn(wx, (float)g.w, wy);
+                const unsigned bit = 1u << (idx[u] & 31);
+                const unsigned old = atomicOr(&wall_bits[idx[u] >> 5], bit);
+                first[u] = !(old & bit);
             }
         }
+        if (pose_from_ext) pdl_wait();          // every -1 of k_map_free has landed
+        int8_t v[kWallPerThread];
+#pragma unroll
+        for (int u = 0; u < kWallPerThread; u++) v[u] = first[u] ? grid[idx[u]] : (int8_t)0;
+#pragma unroll
+        for (int u = 0; u < kWallPerThread; u++)
+            if (first[u]) { grid[idx[u]] = clamp_add(v[u], kOccupiedWeight); mine++; }
     }
-    int c = __syncthreads_count(mine);
+    __shared__ int s_wall;
+    if (threadIdx.x == 0) s_wall = 0;
+    __syncthreads();
+    if (mine) atomicAdd(&s_wall, mine);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        if (c) atomicAdd(&counters[1], c);
-        __threadfence();
-        if (atomicAdd(&counters[3], 1) == (int)gridDim.x - 1) {
-            res->n_free = atomicAdd(&counters[0], 0); res->n_wall = atomicAdd(&counters[1], 0);
-            res->n_slow = atomicAdd(&counters[2], 0);
-            res->n_wide = counters[6]; res->n_windows = counters[7];
-            counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
-        }
+        res->n_free = __ldcg(&counters[0]); res->n_wall = s_wall;
+        res->n_slow = __ldcg(&counters[2]);
+        res->n_wide = __ldcg(&counters[6]); res->n_windows = __ldcg(&counters[7]);
+        counters[0] = 0; counters[1] = 0; counters[2] = 0;
+        counters[10] = counters[10] + 1;         // closes this map update's epoch (k_map_free's cell stamps)
     }
 }
 

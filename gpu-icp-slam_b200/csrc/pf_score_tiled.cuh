@@ -277,12 +277,12 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     }
     if (slow) wk->slow[sbase + __popc(sm_ & ((1u << lane) - 1))] = j;
     int last = 0;
-    __threadfence();                           // every lane's entries before the group is counted as done
+    fence_gpu();                           // every lane's entries before the group is counted as done
     __syncwarp();
     if (lane == 0) last = atomicAdd(&tw->done, 1) == n_groups - 1;
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-    __threadfence();
+    fence_gpu();
 
     // ---- last warp: compact.  Non-empty windows in slot order with their work prefix ...
     int n_win = 0;
@@ -319,7 +319,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
     // ... and the stage table of k_score_staged: tiled stages of kStageWindows windows, then the wide and the slow beams
     // in stages of kStageWindows * 32 beams; per stage the units of the work line before it, and its first block
     if (staged_groups > 0) {
-        __threadfence(); __syncwarp();
+        fence_gpu(); __syncwarp();
         const int SB = stage_windows * kChunkBeams;
         const int n_t = (n_win + stage_windows - 1) / stage_windows, n_w = (nf + SB - 1) / SB, n_s = (ns + SB - 1) / SB;
         const int n_st = min(n_t + n_w + n_s, kMaxStages);
@@ -339,7 +339,7 @@ k_tile_prep(const StepParams *__restrict__ sp, const float *__restrict__ angle,
             if (st < n_st) tw->stage[st] = make_int4(kind, first, nb, run + units - own);
             run += __shfl_sync(0xffffffffu, units, 31);
         }
-        __threadfence(); __syncwarp();
+        fence_gpu(); __syncwarp();
         // Blocks per stage: proportional to the stage's units, at least one; the blocks left over by rounding down go,
         // one at a time, to the stage with the most units per block (lane l keeps stages l, l + 32, ...).
         const int aligned = staged_blocks >= 2 * n_st ? 1 : 0;
@@ -775,13 +775,13 @@ k_score_combine_rows(const int *__restrict__ partial, int n_rows, int n, int gid
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; w++) { mn = min(mn, smin[w]); mk = smax[w] > mk ? smax[w] : mk; }
         blk_min[blockIdx.x] = mn; blk_maxkey[blockIdx.x] = mk;
-        __threadfence();
+        fence_gpu();
         s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
     // last block: thrust::minmax_element's result over all blocks (k_extrema folded in)
-    __threadfence();
+    fence_gpu();
     mn = 0x7fffffff; mk = (long long)0x8000000000000000ull;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
         mn = min(mn, __ldcg(&blk_min[i]));

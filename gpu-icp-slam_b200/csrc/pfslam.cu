@@ -58,6 +58,7 @@ struct pfslam_engine {
     int *fit = nullptr;
     int8_t *grid = nullptr;
     unsigned *free_bits = nullptr, *wall_bits = nullptr;
+    unsigned *free_stamp = nullptr; // grid path: per-cell epoch stamps of k_map_free's claims (never cleared between frames)
     size_t bits_bytes = 0;
     float *scan = nullptr, *angle = nullptr;
     int *blk_min = nullptr; long long *blk_maxkey = nullptr;
@@ -77,6 +78,8 @@ struct pfslam_engine {
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
+    bool tail_fused = false;       // PFSLAM_TAIL=fused: weights + prefix + resample as one launch (k_weights_resample, measured slower)
+    int n_sms = 0;
     bool staged = false;           // scorer generation: k_score_tiled (default) or k_score_staged (PFSLAM_TILED_KERNEL=staged)
     int tiled_grid = 0;            // k_score_tiled grid: SMs x resident blocks per SM
     // pinned host staging
@@ -207,7 +210,7 @@ int pfslam_destroy(pfslam_engine *e)
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->x); cudaFree(e->w); cudaFree(e->fit); cudaFree(e->grid);
-    cudaFree(e->free_bits); cudaFree(e->wall_bits); cudaFree(e->scan); cudaFree(e->angle);
+    cudaFree(e->free_bits); cudaFree(e->wall_bits); cudaFree(e->free_stamp); cudaFree(e->scan); cudaFree(e->angle);
     cudaFree(e->blk_min); cudaFree(e->blk_maxkey); cudaFree(e->ext_local);
     if (e->ext_all != e->ext_local) cudaFree(e->ext_all);
     cudaFree(e->tiles_local);
@@ -249,6 +252,7 @@ static int engine_alloc(pfslam_engine *e)
     e->bits_bytes = ((ncell + 31) / 32) * 4;
     CUDA_TRY(cudaMalloc(&e->free_bits, e->bits_bytes));
     CUDA_TRY(cudaMalloc(&e->wall_bits, e->bits_bytes));
+    CUDA_TRY(cudaMalloc(&e->free_stamp, sizeof(unsigned) * (size_t)ncell));
     CUDA_TRY(cudaMalloc(&e->scan, sizeof(float) * (e->cfg.n_beams + 32)));
     CUDA_TRY(cudaMalloc(&e->angle, sizeof(float) * (e->cfg.n_beams + 32)));
     e->n_score_blocks = score_partial_count(n);
@@ -301,7 +305,7 @@ static int engine_alloc(pfslam_engine *e)
         e->peer_base[x.rank] = e->xreg;
     }
     CUDA_TRY(cudaMalloc(&e->res, sizeof(FrameResult)));
-    CUDA_TRY(cudaMalloc(&e->counters, sizeof(int) * 8));
+    CUDA_TRY(cudaMalloc(&e->counters, sizeof(int) * 16));
     CUDA_TRY(cudaMalloc(&e->fwork, sizeof(ScoreFilteredWork)));
     CUDA_TRY(cudaMalloc(&e->score_partial, sizeof(int) * (size_t)score_tiled_rows() * n));
     CUDA_TRY(cudaMalloc(&e->twork, sizeof(TiledWork)));
@@ -342,10 +346,11 @@ static int engine_alloc(pfslam_engine *e)
     CUDA_TRY(cudaMemsetAsync(e->grid, -100 & 0xff, ncell, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->free_stamp, 0, sizeof(unsigned) * (size_t)e->geom.w * e->geom.h, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->scan, 0, sizeof(float) * (e->cfg.n_beams + 32), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->fit, 0, sizeof(int) * n, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->res, 0, sizeof(FrameResult), e->stream));
-    CUDA_TRY(cudaMemsetAsync(e->counters, 0, sizeof(int) * 8, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->counters, 0, sizeof(int) * 16, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->fwork, 0, sizeof(ScoreFilteredWork), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->tiles_local, 0, sizeof(float) * e->tiles_block, e->stream));
     k_init_beams<<<ceil_div(e->cfg.n_beams + 32, 128), 128, 0, e->stream>>>(e->angle, e->cfg.n_beams + 32);
@@ -369,7 +374,7 @@ static int preload_kernels()
     PF_PRELOAD(k_beam_prep); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<256, 4>)); CUDA_TRY(cudaFuncGetAttributes(&a, k_score_tiled<512, 2>)); PF_PRELOAD(k_score_fast); PF_PRELOAD(k_score_exact);
     CUDA_TRY(cudaFuncGetAttributes(&a, staged_kernel()));
     PF_PRELOAD(k_score_combine); PF_PRELOAD(k_score_combine_rows); PF_PRELOAD(k_extrema);
-    PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
+    PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_weights_resample); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
     PF_PRELOAD(k_score_kd<0>); PF_PRELOAD(k_score_kd<1>); PF_PRELOAD(k_score_kd<2>); PF_PRELOAD(k_kd_shadow<1>); PF_PRELOAD(k_kd_shadow<2>); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
     PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
     PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait); PF_PRELOAD(k_publish_result);
@@ -439,6 +444,8 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     // graph it still finishes ~10 us ahead of k_score_staged (1 block per SM, 5 windows resident, all beams in one kernel),
     // whose block-wide stage loads nothing else on the SM can hide; PFSLAM_TILED_KERNEL=staged selects the latter
     { const char *tk = getenv("PFSLAM_TILED_KERNEL"); e->staged = tk && strcmp(tk, "staged") == 0; }
+    { const char *tl = getenv("PFSLAM_TAIL"); e->tail_fused = tl && strcmp(tl, "fused") == 0; }
+    if (cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess) e->n_sms = 0;
     { const char *dg = getenv("PFSLAM_STAGED_DEBUG"); const int v = dg ? atoi(dg) : 0; cudaMemcpyToSymbol(g_staged_dbg, &v, sizeof v); }
     int rc = engine_alloc(e);
     if (rc != PFSLAM_OK) { std::string keep = g_last_error; pfslam_destroy(e); g_last_error = keep; return rc; }
@@ -803,8 +810,7 @@ static int launch_prefix(pfslam_engine *e)
 
 static int clear_map_masks(pfslam_engine *e, cudaStream_t st)
 {
-    CUDA_TRY(cudaMemsetAsync(e->free_bits, 0, e->bits_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(e->wall_bits, 0, e->bits_bytes, st));      // (the free pass claims by epoch stamp)
     return PFSLAM_OK;
 }
 
@@ -817,11 +823,11 @@ static int launch_map(pfslam_engine *e, cudaStream_t st, int pose_from_ext)
         k_xc_wait<<<1, 32, 0, st>>>(*e->cur_xc, e->sp, kXcExt, e->res);
         e->launches++;
     }
-    k_map_free<<<e->cfg.n_beams, 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_bits,
+    k_map_free<<<e->cfg.n_beams, 128, 0, st>>>(e->grid, e->geom, e->res, scan, e->angle, e->free_stamp,
                                                e->counters, *e->cur_xc, pose_from_ext);
     if (e->laps_on) e->laps.mark(st, kLapMapFree);
     // dependent launch of k_map_free (same stream, directly behind it) unless a lap marker sits in between
-    launch_k(!e->laps_on, k_map_wall, dim3(ceil_div(e->cfg.n_beams, 128)), dim3(128), 0, st, e->grid, e->geom, e->res, scan, e->angle,
+    launch_k(!e->laps_on, k_map_wall, dim3(1), dim3(kWallThreads), 0, st, e->grid, e->geom, e->res, scan, e->angle,
              e->cfg.n_beams, e->wall_bits, e->counters, *e->cur_xc, pose_from_ext);
     if (e->laps_on) e->laps.mark(st, kLapMapWall);
     e->launches += 2;
@@ -1019,6 +1025,18 @@ static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
     return ph_resample(e, frame);
 }
 
+// PFSLAM_TAIL=fused: one launch for weights / prefix / resample (k_weights_resample, a grid-wide barrier in the middle).
+// It needs every one of its n_tiles blocks resident at the same time: allowed while that is at most two 256-thread
+// blocks per SM -- a quarter of the thread slots -- so the map branch's kernels next to it can never lock it out.
+// Not the default: with one block per tile the resampler's random probes run on n_tiles SMs only, and bench.py
+// measures 110.9 us per step against 100.3 us for the three-kernel sequence.
+static bool tail_fusable(pfslam_engine *e)
+{
+    const bool local_or_peer = e->n_ranks == 1 || e->cur_xc->parity_mask;
+    return e->tail_fused && local_or_peer && e->cfg.path == PFSLAM_PATH_GRID2D &&
+           e->n_tiles <= 2 * e->n_sms && e->n_tiles * e->n_ranks <= kFusedPrefixMaxTiles;
+}
+
 static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
 {
     int rc;
@@ -1042,10 +1060,20 @@ static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
     CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork[2], 0));
     if ((rc = launch_map(e, e->aux, 1))) return rc;
     CUDA_TRY(cudaEventRecord(e->ev_join[1], e->aux));
-    if ((rc = ph_weights(e))) return rc;
-    e->resample_follows_weights = e->prefix_fused;
-    if ((rc = launch_prefix(e))) return rc;
-    if ((rc = ph_resample(e, frame))) return rc;
+    if (tail_fusable(e)) {
+        // weights + tile scans + prefix + resample as one launch with a grid-wide barrier (k_weights_resample)
+        const int n_sync = (e->cfg.quirks & PFSLAM_QUIRK_Q1_HALF_WEIGHT_SYNC) ? (e->n_global + 1) / 2 : e->n_global;
+        launch_k(e->score_mode == PFSLAM_SCORE_TILED, k_weights_resample, dim3(e->n_tiles), dim3(kScanThreads), 0, e->stream,
+                 *e->cur_xc, e->sp, e->fit, e->w, e->n, e->gidx0, n_sync, e->n_tiles, e->tiles_local, e->n_global, e->prefix,
+                 e->res, reinterpret_cast<unsigned long long *>(e->counters + 8), e->x, e->y, e->th);
+        e->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        if ((rc = ph_weights(e))) return rc;
+        e->resample_follows_weights = e->prefix_fused;
+        if ((rc = launch_prefix(e))) return rc;
+        if ((rc = ph_resample(e, frame))) return rc;
+    }
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[1], 0));
     return PFSLAM_OK;
 }
@@ -1464,8 +1492,9 @@ int pfslam_set_kd(pfslam_engine *e, const void *nodes_in, int32_t n_nodes)
 
 int64_t pfslam_launch_count(pfslam_engine *e) { return e ? e->launches : 0; }
 
-static const char *const kTraceNames[kTrCount] = {"k_motion", "k_tile_prep", "k_score_staged", "k_score_fast", "k_score_combine_rows",
-                                                  "k_weights_scan", "k_resample", "k_map_free", "k_map_wall", "k_publish_result"};
+static const char *const kTraceNames[kTrCount] = {"k_motion", "k_tile_prep", "k_score_tiled", "k_score_fast", "k_score_combine_rows",
+                                                  "k_weights_scan", "k_resample", "k_map_free", "k_map_wall", "k_publish_result",
+                                                  "mark0", "mark1", "mark2", "mark3", "mark4", "mark5"};
 const char *pfslam_trace_name(int32_t id) { return id >= 0 && id < kTrCount ? kTraceNames[id] : ""; }
 
 // on != 0: switch the in-kernel timeline on and reset it; out (optional, 2 * PFSLAM_TRACE_COUNT words): the [first

@@ -154,7 +154,7 @@ def debug_trig(x, device=0):
     return c, s
 
 
-TRACE_COUNT = 10
+TRACE_COUNT = 16
 
 
 def debug_trace(on=True, read=False):

@@ -215,7 +215,7 @@ const char *pfslam_lap_name(int32_t id);
 /* tuning hook: in-graph timeline.  While on, every kernel of the 2D step folds %globaltimer into a [first entry, last
  * exit] pair; (on, out): copy the pairs recorded so far (2 * PFSLAM_TRACE_COUNT words, nanoseconds), then reset.
  * The caller synchronises the engine's stream around the call. */
-#define PFSLAM_TRACE_COUNT 10
+#define PFSLAM_TRACE_COUNT 16
 int  pfslam_debug_trace(int32_t on, uint64_t *out);
 const char *pfslam_trace_name(int32_t id);
 

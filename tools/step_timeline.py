@@ -24,7 +24,7 @@ with g.ParticleFilter(n) as pf:
     while time.time() - t0 < 2.5:                      # map built, clocks at their maximum
         f += 1
         pf.step(sc[1 + (f - 1) % last], f)
-    rows = {}
+    rows = {0: {}, 1: {}}                               # by "this step resampled"
     for k in range(steps):
         f += 1
         pf.synchronize()
@@ -34,12 +34,18 @@ with g.ParticleFilter(n) as pf:
         tr = engine.debug_trace(True, read=True)
         t_first = min(a for a, _ in tr.values())
         for name, (a, b) in tr.items():
-            rows.setdefault(name, []).append(((a - t_first) / 1e3, (b - t_first) / 1e3))
+            rows[int(r.resampled)].setdefault(name, []).append(((a - t_first) / 1e3, (b - t_first) / 1e3))
     engine.debug_trace(False)
-    print("last frame: %d windows, %d wide beams, %d exact re-evaluations, resampled %d" % (r.n_windows, r.n_wide_beams, r.n_slow_evals, r.resampled))
-    print("| kernel | first block in (us) | last block out (us) | span (us) |")
-    print("|---|---|---|---|")
-    for name, v in sorted(rows.items(), key=lambda kv: np.mean([a for a, _ in kv[1]])):
-        a, b = np.mean([x for x, _ in v]), np.mean([y for _, y in v])
-        print("| %s | %.1f | %.1f | %.1f |" % (name, a, b, b - a))
-    print("step (first entry -> last exit): %.1f us" % np.mean([max(rows[nm][i][1] for nm in rows if len(rows[nm]) > i) for i in range(steps)]))
+    print("last frame: %d windows, %d wide beams, %d exact re-evaluations" % (r.n_windows, r.n_wide_beams, r.n_slow_evals))
+    for kind in (0, 1):
+        rk = rows[kind]
+        if not rk:
+            continue
+        cnt = max(len(v) for v in rk.values())
+        print("\n%d steps that %s:" % (cnt, "resampled" if kind else "did not resample"))
+        print("| kernel | first block in (us) | last block out (us) | span (us) |")
+        print("|---|---|---|---|")
+        for name, v in sorted(rk.items(), key=lambda kv: np.mean([a for a, _ in kv[1]])):
+            a, b = np.mean([x for x, _ in v]), np.mean([y for _, y in v])
+            print("| %s | %.1f | %.1f | %.1f |" % (name, a, b, b - a))
+        print("step (first entry -> last exit): %.1f us" % np.mean([max(rk[nm][i][1] for nm in rk if len(rk[nm]) > i) for i in range(cnt)]))
