@@ -409,7 +409,10 @@ def run_ours(args):
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     launches = pf.launch_count - l0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(step_ms)
+    # the filter settles into resampling every other frame: even / odd steps separate the two kinds of step
+    even_odd_ms = [float(np.mean(step_ms[0::2])), float(np.mean(step_ms[1::2]))] if K >= 2 else None
     r1 = eng0.fetch_result()
     resampled_steps = r1.resample_count - resample_count0
     # time this rank's kernels spent waiting for the peers' extrema / tile sums, per step (in-kernel %globaltimer stamps)
@@ -516,7 +519,7 @@ def run_ours(args):
                        "exchange": ("none (single GPU)" if world == 1 else
                                     "in-kernel stores/loads over NVLink peer memory, whole step = 1 CUDA graph per rank" if args.exchange == "peer"
                                     else "3 NCCL all-gathers between the step's phases")},
-            "resampled_steps": int(resampled_steps),
+            "resampled_steps": int(resampled_steps), "ms_per_step_even_odd": even_odd_ms,
             "exchange_wait_us_per_step": ({"extrema": wait_ext_us, "tiles": wait_tiles_us,
                                            "note": "max over ranks of the time the step's kernels spent in the two peer waits"} if world > 1 else None),
             "value_back_to_back": K / (b2b_ms * 1e-3) * scale,

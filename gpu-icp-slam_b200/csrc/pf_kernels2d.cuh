@@ -431,6 +431,8 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
     TraceScope trace_scope(kTrWeights);
     __shared__ float s_wtot[8], s_wmax[8];
     __shared__ int s_last;
+    pdl_trigger();                              // k_resample's blocks may be staged (measured: 0.3 us per step better than
+                                                // staging them after the tile scans)
     pdl_wait();                                 // scores and extrema of k_score_combine_rows
     const int seq = sp->seq;
     if (xc.parity_mask) {
@@ -467,8 +469,6 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
     float t2 = tile_scan4(q, lm2, s_wtot, s_wmax);
     float t1 = tile_scan4(e, lm, s_wtot, s_wmax);
     trace_mark(kTrMark4);                       // tile scans done
-    pdl_trigger();                              // k_resample's blocks may be staged now (not earlier: they would sit on
-                                                // registers the map update's blocks need while this kernel works)
     if (!xc.parity_mask) {
         float *lm_out = tiles_local + xc.lm_off;
 #pragma unroll
