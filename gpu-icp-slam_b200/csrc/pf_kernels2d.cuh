@@ -207,6 +207,24 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
     }
 }
 
+// Peer-memory shards: copy this rank's pre-resample snapshot (written by k_motion into slot [parity][rank] of its own
+// exchange region) into the same slot of every peer's region -- one coalesced 16-byte store per particle and peer.
+// Runs on the side branch under the scoring kernels and completes before this rank's k_weights_scan raises its tile
+// flags, so a rank that has seen everybody's tile flags (every k_resample has) holds everybody's snapshot.
+// Small blocks (128 threads, few registers, no shared memory) on a grid-stride loop: they fit next to the three resident
+// blocks per SM of the tiled scorer instead of displacing one of them.
+__global__ void __launch_bounds__(128)
+k_snapshot_push(const Xchg xc, const StepParams *__restrict__ sp, int n)
+{
+    const long long slot0 = ((long long)(sp->seq & 1) * xc.n_ranks + xc.rank) * n;          // float4 index in the snapshot area
+    const float4 *__restrict__ mine = reinterpret_cast<const float4 *>(xc.peer[xc.rank] + xc.off_snap) + slot0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 v = mine[i];
+        for (int r = 0; r < xc.n_ranks; r++)
+            if (r != xc.rank) reinterpret_cast<float4 *>(xc.peer[r] + xc.off_snap)[slot0 + i] = v;
+    }
+}
+
 // host API step: the frame result goes to the pinned, device-mapped result record from the last node of the graph
 __global__ void k_publish_result(const FrameResult *__restrict__ res, const StepParams *__restrict__ sp)
 {

@@ -4,14 +4,17 @@
 // The reference is single-GPU; sharding is new.  Per frame a shard needs from the others
 //   (1) the score extrema {min, max, first arg-max, its pose}              32 B per rank
 //   (2) per-tile weight sums and the tile-local CDF values                  ~4 B per particle
-//   (3) the pre-resample pose of whatever particle its resampler draws     12 B per local particle
+//   (3) the pre-resample pose of whatever particle its resampler draws     16 B per particle
 // Every engine owns one "exchange region" (a single cudaMalloc, IPC-exportable) with the same layout
 // on every rank.  Producers STORE (1) and (2) straight into every peer's region from the kernel that
 // computes them (k_score_combine_rows / k_extrema, k_weights_scan), then raise a per-(kind, source
 // rank) flag in the peer's region with the step's sequence number; the first consumer kernel of the
-// step spins (bounded) on its own region's flags.  (3) is PULLED: k_resample loads the drawn
-// particle's pose from the owner's snapshot over NVLink.  No NCCL call, no host round trip: the
-// sharded step is the same single CUDA graph as the single-GPU step.
+// step spins (bounded) on its own region's flags.  (3) is PUSHED whole: every rank copies its 16 B/particle
+// pre-resample snapshot into every peer's region with coalesced stores from a side-branch kernel that runs under the
+// scoring (k_snapshot_push), and the resampler gathers locally.  (Round 1 PULLED the drawn poses one by one over
+// NVLink: ~30 k random 16-byte remote reads per GPU on a resampling step cost 9 us on 2 GPUs and more on 8 --
+// PFSLAM_SNAPSHOT=pull keeps that mode.)  No NCCL call, no host round trip: the sharded step is the same single
+// CUDA graph as the single-GPU step.
 //
 // Buffers are double-buffered by step parity.  That is enough because the shards run in lock step:
 // a rank publishes extrema(s+1) only after it has seen every rank's tiles(s), and tiles(s+1) only
@@ -51,7 +54,7 @@ struct Xchg {
     int     *flags;               // [kind][kMaxRanks] sequence numbers, written by the peers
     // every rank's region (peer memory) and the byte offsets of the parts inside a region
     unsigned char *peer[kMaxRanks];
-    long long off_ext, off_tiles, off_flags;
+    long long off_ext, off_tiles, off_flags, off_snap;
     const float *pose_src[kMaxRanks];   // resample gather source per owner rank (parity 0)
 };
 

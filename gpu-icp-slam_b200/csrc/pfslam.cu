@@ -78,6 +78,7 @@ struct pfslam_engine {
     bool bounds_valid = false;     // cloud bounds in twork were produced by k_motion for the current poses
     CUtensorMap tmap;
     int score_mode = 0;            // effective mode (TILED falls back to FILTERED when unsupported)
+    bool snap_push = true;         // peer shards: snapshots pushed to every peer (k_snapshot_push); PFSLAM_SNAPSHOT=pull: gathered remotely
     bool tail_fused = false;       // PFSLAM_TAIL=fused: weights + prefix + resample as one launch (k_weights_resample, measured slower)
     int n_sms = 0;
     bool staged = false;           // scorer generation: k_score_tiled (default) or k_score_staged (PFSLAM_TILED_KERNEL=staged)
@@ -289,19 +290,19 @@ static int engine_alloc(pfslam_engine *e)
         e->xoff_ext = up(sizeof(int) * 2 * kMaxRanks);
         e->xoff_tiles = up(e->xoff_ext + sizeof(Extrema) * 2 * kMaxRanks);
         e->xoff_snap = up(e->xoff_tiles + sizeof(float) * 2 * e->n_ranks * tb);
-        e->xreg_bytes = up(e->xoff_snap + sizeof(float) * 2 * 4 * (size_t)n);
+        e->xreg_bytes = up(e->xoff_snap + sizeof(float) * 2 * 4 * (size_t)n * e->n_ranks);     // snapshots [parity][rank][n] float4
         CUDA_TRY(cudaMalloc(&e->xreg, e->xreg_bytes));
         CUDA_TRY(cudaMemsetAsync(e->xreg, 0, e->xreg_bytes, e->stream));
         Xchg &x = e->xc_p2p;
         x.n_ranks = e->n_ranks; x.rank = e->gidx0 / n; x.parity_mask = 1;
         const char *to = getenv("PFSLAM_PEER_TIMEOUT_MS");
         x.timeout_ms = to ? (unsigned)atoi(to) : 10000u;
-        x.tiles_block = (long long)tb; x.sum_off = n; x.lm_off = 0; x.snap_stride = 4ll * n; x.snap_aos = 1;
+        x.tiles_block = (long long)tb; x.sum_off = n; x.lm_off = 0; x.snap_stride = 4ll * n * e->n_ranks; x.snap_aos = 1;
         x.ext_all = reinterpret_cast<Extrema *>(e->xreg + e->xoff_ext);
         x.tiles_all = reinterpret_cast<float *>(e->xreg + e->xoff_tiles);
-        x.snap = reinterpret_cast<float *>(e->xreg + e->xoff_snap);
+        x.snap = reinterpret_cast<float *>(e->xreg + e->xoff_snap) + 4ll * n * x.rank;          // own slot of parity 0
         x.flags = reinterpret_cast<int *>(e->xreg + e->xoff_flags);
-        x.off_ext = (long long)e->xoff_ext; x.off_tiles = (long long)e->xoff_tiles; x.off_flags = (long long)e->xoff_flags;
+        x.off_ext = (long long)e->xoff_ext; x.off_tiles = (long long)e->xoff_tiles; x.off_flags = (long long)e->xoff_flags; x.off_snap = (long long)e->xoff_snap;
         e->peer_base[x.rank] = e->xreg;
     }
     CUDA_TRY(cudaMalloc(&e->res, sizeof(FrameResult)));
@@ -377,7 +378,7 @@ static int preload_kernels()
     PF_PRELOAD(k_weights_scan); PF_PRELOAD(k_weights_resample); PF_PRELOAD(k_prefix); PF_PRELOAD(k_resample); PF_PRELOAD(k_map_free); PF_PRELOAD(k_map_wall);
     PF_PRELOAD(k_score_kd<0>); PF_PRELOAD(k_score_kd<1>); PF_PRELOAD(k_score_kd<2>); PF_PRELOAD(k_kd_shadow<1>); PF_PRELOAD(k_kd_shadow<2>); PF_PRELOAD(k_icp); PF_PRELOAD(k_kd_mark); PF_PRELOAD(k_bits_count); PF_PRELOAD(k_bits_offsets);
     PF_PRELOAD(k_bits_scatter); PF_PRELOAD(k_kd_points_nn); PF_PRELOAD(k_kd_weights); PF_PRELOAD(k_kd_insert);
-    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait); PF_PRELOAD(k_publish_result);
+    PF_PRELOAD(k_kd_finish); PF_PRELOAD(k_kd_nn); PF_PRELOAD(k_xc_wait); PF_PRELOAD(k_publish_result); PF_PRELOAD(k_snapshot_push);
 #undef PF_PRELOAD
     return PFSLAM_OK;
 }
@@ -444,6 +445,7 @@ int pfslam_create(const pfslam_config *cfg, pfslam_engine **out)
     // graph it still finishes ~10 us ahead of k_score_staged (1 block per SM, 5 windows resident, all beams in one kernel),
     // whose block-wide stage loads nothing else on the SM can hide; PFSLAM_TILED_KERNEL=staged selects the latter
     { const char *tk = getenv("PFSLAM_TILED_KERNEL"); e->staged = tk && strcmp(tk, "staged") == 0; }
+    { const char *sm = getenv("PFSLAM_SNAPSHOT"); e->snap_push = !(sm && strcmp(sm, "pull") == 0); }
     { const char *tl = getenv("PFSLAM_TAIL"); e->tail_fused = tl && strcmp(tl, "fused") == 0; }
     if (cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess) e->n_sms = 0;
     { const char *dg = getenv("PFSLAM_STAGED_DEBUG"); const int v = dg ? atoi(dg) : 0; cudaMemcpyToSymbol(g_staged_dbg, &v, sizeof v); }
@@ -577,7 +579,9 @@ int pfslam_exchange_ready(pfslam_engine *e)
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     for (int r = 0; r < e->n_ranks; r++) {
         e->xc_p2p.peer[r] = static_cast<unsigned char *>(e->peer_base[r]);
-        e->xc_p2p.pose_src[r] = reinterpret_cast<const float *>(e->xc_p2p.peer[r] + e->xoff_snap);
+        // rank r's snapshot, parity 0: the copy pushed into this rank's own region, or (pull mode) r's own slot over NVLink
+        unsigned char *from = e->snap_push ? e->xreg : e->xc_p2p.peer[r];
+        e->xc_p2p.pose_src[r] = reinterpret_cast<const float *>(from + e->xoff_snap) + 4ll * e->n * r;
     }
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
@@ -605,6 +609,16 @@ int pfslam_upload_scan(pfslam_engine *e, const float *scan_host)
     memcpy(e->h_scan, scan_host, sizeof(float) * e->cfg.n_beams);
     CUDA_TRY(cudaMemcpyAsync(e->scan, e->h_scan, sizeof(float) * e->cfg.n_beams,
                              cudaMemcpyHostToDevice, e->stream));
+    return PFSLAM_OK;
+}
+
+// peer-memory shards: this rank's snapshot into every peer's region (pf_xchg.cuh)
+static int push_snapshot(pfslam_engine *e, cudaStream_t st)
+{
+    if (!e->cur_xc->parity_mask || !e->snap_push) return PFSLAM_OK;
+    k_snapshot_push<<<std::min(ceil_div(e->n, 128), std::max(e->n_sms, 1)), 128, 0, st>>>(*e->cur_xc, e->sp, e->n);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
     return PFSLAM_OK;
 }
 
@@ -1008,6 +1022,7 @@ static int kd_step(pfslam_engine *e, const float *scan_dev, int32_t frame)
         return kd_update_map(e);
     }
     if ((rc = ph_motion(e, frame))) return rc;
+    if ((rc = push_snapshot(e, e->stream))) return rc;
     const bool prof = e->prof_on && e->prof_n < (int)e->prof_ev.size() / 2;
     if (prof) cudaEventRecord(e->prof_ev[2 * e->prof_n], e->stream);
     launch_score_kd(e);
@@ -1043,6 +1058,7 @@ static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
     if (e->laps_on) e->laps.mark(e->stream, kLapStart);
     if ((rc = ph_motion(e, frame))) return rc;
     if (!(e->overlap && !e->laps_on)) {
+        if ((rc = push_snapshot(e, e->stream))) return rc;
         if ((rc = ph_score(e, scan_dev))) return rc;
         if ((rc = ph_weights(e))) return rc;
         if ((rc = ph_map(e, scan_dev))) return rc;
@@ -1055,6 +1071,7 @@ static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
     CUDA_TRY(cudaEventRecord(e->ev_fork[1], e->stream));
     CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork[1], 0));
     if ((rc = clear_map_masks(e, e->aux))) return rc;      // off the critical path: overlaps the scoring
+    if ((rc = push_snapshot(e, e->aux))) return rc;        // ... and so does the snapshot exchange (joined before the combine kernel)
     if ((rc = ph_score(e, scan_dev))) return rc;
     CUDA_TRY(cudaEventRecord(e->ev_fork[2], e->stream));
     CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork[2], 0));
