@@ -505,7 +505,7 @@ k_weights_scan(const Xchg xc, const StepParams *__restrict__ sp, const int *__re
         __syncthreads();          // thread 0's system fence below then covers the whole block's stores
     }
     if (threadIdx.x == 0) {
-        if (xc.parity_mask) __threadfence_system(); else fence_gpu();
+        if (xc.parity_mask) xc_fence_sys(); else fence_gpu();
         s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
@@ -725,7 +725,7 @@ k_weights_resample(const Xchg xc, const StepParams *__restrict__ sp, const int *
     // ---- grid-wide barrier -------------------------------------------------------------------------
     if (xc.parity_mask) {
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            xc_fence_sys();
             const unsigned long long ticket = atomicAdd(arrivals, 1ull);
             if (ticket % gridDim.x == gridDim.x - 1) xc_signal(xc, kXcTiles, seq);
         }

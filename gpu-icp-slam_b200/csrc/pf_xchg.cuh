@@ -68,6 +68,9 @@ __device__ __forceinline__ unsigned long long xc_now_ns()
 // the consumer fences ONCE after the flag has arrived; producers fence once and then raise every peer's flag
 // with relaxed stores (a release store per peer would repeat the fence -- one NVLink round trip -- per peer,
 // which is what made the exchange cost grow with the rank count).
+// release / acquire fence at system scope (the sequentially consistent __threadfence_system() is not needed for
+// the store -> fence -> flag | flag -> fence -> load hand-overs)
+__device__ __forceinline__ void xc_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ int xc_ld_relaxed(const int *p)
 {
     int v;
@@ -127,7 +130,7 @@ __device__ __forceinline__ bool xc_wait_warp(const Xchg &xc, int kind, int seq)
             }
         }
     }
-    if (kind != kXcExt) __threadfence_system();   // acquire: what the producers wrote before their flags is visible now
+    if (kind != kXcExt) xc_fence_sys();   // acquire: what the producers wrote before their flags is visible now
     return __all_sync(0xffffffffu, ok);
 }
 
@@ -135,7 +138,7 @@ __device__ __forceinline__ bool xc_wait_warp(const Xchg &xc, int kind, int seq)
 // stores visible system-wide ONCE, then raise this rank's flag in every peer's region.
 __device__ __forceinline__ void xc_signal(const Xchg &xc, int kind, int seq)
 {
-    __threadfence_system();
+    xc_fence_sys();
     for (int r = 0; r < xc.n_ranks; r++)
         xc_st_relaxed(reinterpret_cast<int *>(xc.peer[r] + xc.off_flags) + kind * kMaxRanks + xc.rank, seq);
 }
