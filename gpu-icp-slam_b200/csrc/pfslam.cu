@@ -98,7 +98,7 @@ struct pfslam_engine {
     KdSearch *kds = nullptr;               // 16-byte search shadow of kd (planar trees)
     int kd_size_ub = 0;                    // host-side upper bound of the device tree size
     bool kd_flat = true;                   // every node has z == 0 and a valid axis: the scorer walks the shadow
-    int kd_walk = 1;                       // shadow format / visit body: 1 (default), 2 = branch-free visit (PFSLAM_KD_WALK=2)
+    int kd_walk = 2;                       // shadow format / visit body: 2 = branch-free visit (default), 1 = round 1's (PFSLAM_KD_WALK=1)
     KdState *ks = nullptr;
     int *bits_blk = nullptr; int n_bits_blk = 0;
     int *free_cells = nullptr, *wall_cells = nullptr; int pc_cap = 8192;
@@ -321,7 +321,7 @@ static int engine_alloc(pfslam_engine *e)
         e->kd_cap = e->cfg.kd_capacity > 0 ? e->cfg.kd_capacity : (1 << 21);
         CUDA_TRY(cudaMalloc(&e->kd, sizeof(KdNode) * (size_t)e->kd_cap));
         CUDA_TRY(cudaMalloc(&e->kds, sizeof(KdSearch) * (size_t)e->kd_cap));
-        { const char *kw = getenv("PFSLAM_KD_WALK"); e->kd_walk = (kw && atoi(kw) == 2) ? 2 : 1; }
+        { const char *kw = getenv("PFSLAM_KD_WALK"); e->kd_walk = (kw && atoi(kw) == 1) ? 1 : 2; }
         CUDA_TRY(cudaMalloc(&e->ks, sizeof(KdState)));
         CUDA_TRY(cudaMemsetAsync(e->ks, 0, sizeof(KdState), e->stream));
         e->n_bits_blk = ceil_div((int)(e->bits_bytes / 4), kBitsBlockWords);
