@@ -174,3 +174,11 @@ def test_staged_scorer_generation_is_bit_exact_too(scans, monkeypatch, threads):
     sent = np.full(1081, 4294967.0, np.float32)
     seq = [(1, scans[1]), (2, sent), (3, scans[3]), (4, np.full(1081, 25.0, np.float32)), (5, scans[5])]
     _run_pair(1500, scans, seq)
+
+
+def test_fused_tail_kernel_is_bit_exact_too(scans, monkeypatch):
+    """k_weights_resample (PFSLAM_TAIL=fused: weights, tile scans, prefix and resampling in one launch around a
+    grid-wide barrier) is the measured-but-not-default tail; same bits as the oracle, partial last tile included"""
+    monkeypatch.setenv("PFSLAM_TAIL", "fused")
+    _run_pair(2500, scans, [(f, scans[f]) for f in range(1, 40)])
+    _run_pair(5000, scans, [(f, scans[f]) for f in range(1, 24)])

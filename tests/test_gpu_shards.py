@@ -1,8 +1,8 @@
 """Sharded filter over the PEER-MEMORY exchange (csrc/pf_xchg.cuh), exercised on one GPU: R engines in
 one process, each holding N/R particles, wired to each other's exchange regions with
 pfslam_connect_peer and stepped concurrently on their own streams.  The kernels publish extrema and
-weight tiles into each other's regions, spin on the sequence flags and pull resampled poses from
-the owner exactly as they do across GPUs (only the IPC handle plumbing differs; that part is covered
+weight tiles and their pose snapshots into each other's regions and spin on the sequence flags
+exactly as they do across GPUs (only the IPC handle plumbing differs; that part is covered
 by tools/dist_check.py under torchrun on a multi-GPU box).  Every shard must reproduce the
 single-engine oracle bit for bit: SURVEY 8(e) "identical trajectories for 1/2/4/8 GPUs"."""
 import numpy as np
@@ -37,9 +37,15 @@ def step_all(engines, scan, frame):
     return [e.fetch_result() for e in engines]
 
 
-@pytest.mark.parametrize("n_ranks,n_total", [(2, 4096), (4, 8192), (8, 8192)])
-def test_grid_shards_match_single_oracle(scans, n_ranks, n_total):
+@pytest.mark.parametrize("n_ranks,n_total,switches", [
+    (2, 4096, {}), (4, 8192, {}), (8, 8192, {}),
+    (4, 8192, {"PFSLAM_SNAPSHOT": "pull"}),        # resampler loads the drawn poses from the owner (round-2 mid scheme)
+    (4, 8192, {"PFSLAM_TAIL": "fused"}),           # weights + prefix + resample as one kernel with a grid-wide barrier
+])
+def test_grid_shards_match_single_oracle(scans, n_ranks, n_total, switches, monkeypatch):
     import gpu_icp_slam_b200 as g
+    for k, v in switches.items():                  # read when an engine is created
+        monkeypatch.setenv(k, v)
     frames = 30
     of = helpers.OracleFilter(n_total)
     engines = make_shards(g, n_total, n_ranks)
