@@ -128,6 +128,7 @@ struct FrameResult {
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
 // step can be replayed with new values (a 16-byte H2D copy node at the head of the graph)
 struct FrameResult;
+constexpr int kParamsInDeviceMemory = (int)0x80000000;    // StepParams.seq of a by-value argument that is not one
 struct StepParams {
     const float *scan;   // this frame's ranges (device)
     int frame;           // frame number (seeds, kernel.cu:380, :434)
@@ -156,18 +157,26 @@ __device__ __forceinline__ float order_float(int k)
 // resampler gathers from -- `snap` [parity][x | y | theta], null when a host all-gathers it.
 __global__ void __launch_bounds__(256)
 k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, int n,
-         const StepParams *__restrict__ sp, int gidx0, int *__restrict__ bounds,
+         StepParams *sp, int gidx0, int *__restrict__ bounds,
          float *__restrict__ snap, long long snap_stride, int parity_mask, int snap_aos, int *__restrict__ acc_row,
-         const float *__restrict__ scan_src, float *__restrict__ scan_dst, int n_beams, float4 *__restrict__ pcs)
+         const float *__restrict__ scan_src, float *__restrict__ scan_dst, int n_beams, float4 *__restrict__ pcs,
+         const StepParams spv)
 {
     TraceScope trace_scope(kTrMotion);
     __shared__ int s_b[6];
     pdl_trigger();                              // k_tile_prep's blocks may be staged now; they wait for this grid
+    // The step's parameters arrive as a kernel argument of this, the first kernel of the captured step (the host
+    // updates the argument of the graph's kernel node before every launch -- no copy node in front of the graph), and
+    // one thread files them in device memory for the kernels behind it (all of which start after this grid has
+    // completed).  Plain launches and hosts that set the parameters themselves pass kParamsInDeviceMemory.
+    const bool by_value = spv.seq != kParamsInDeviceMemory;
+    const StepParams P = by_value ? spv : *sp;
+    if (by_value && blockIdx.x == 0 && threadIdx.x == 0) *sp = spv;
     // host API step (pfslam_step): the frame's scan is pulled from the pinned, device-mapped staging buffer by the
     // first kernel of the step (nobody reads the device copy before this grid has completed), so the step graph needs
     // no copy node for it
     if (scan_src && blockIdx.x == gridDim.x - 1) {
-        const float *__restrict__ src = sp->scan_src;
+        const float *__restrict__ src = P.scan_src;
         if (src) for (int j = threadIdx.x; j < n_beams; j += blockDim.x) scan_dst[j] = src[j];
     }
     if (threadIdx.x < 6) s_b[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
@@ -175,7 +184,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
     if (i < n) {
-        const int frame = sp->frame;
+        const int frame = P.frame;
         uint32_t st = pf_minstd_seed(pf_seed(frame, gidx0 + i, 0));
         float nx = pf_normal(st, 0.015f);
         float ny = pf_normal(st, 0.015f);
@@ -185,7 +194,7 @@ k_motion(float *__restrict__ x, float *__restrict__ y, float *__restrict__ th, i
         acc_row[i] = 0;                        // the tiled scorer adds into it (pf_score_tiled.cuh)
         if (pcs) { float sn, cs; sincosf(vt, &sn, &cs); pcs[i] = make_float4(vx, vy, cs, sn); }   // ... and reads the pose from here
         if (snap) {
-            float *sn = snap + (long long)(sp->seq & parity_mask) * snap_stride;
+            float *sn = snap + (long long)(P.seq & parity_mask) * snap_stride;
             if (snap_aos) reinterpret_cast<float4 *>(sn)[i] = make_float4(vx, vy, vt, 0.0f);
             else { sn[i] = vx; sn[n + i] = vy; sn[2 * n + i] = vt; }
         }

@@ -109,12 +109,12 @@ k_score_staged(const __grid_constant__ CUtensorMap tmap, const int8_t *__restric
     constexpr int GP = THREADS * PPT;           // particles per group
     constexpr int NWARPS = THREADS / 32;
     constexpr int SB = K * kChunkBeams;         // beams per wide / slow stage
-    const float *__restrict__ scan = sp->scan;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StagedSmem<K, NWARPS> &sm = *reinterpret_cast<StagedSmem<K, NWARPS> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long ts_entry = staged_now();
-    pdl_wait();                                 // k_tile_prep's window table and beam lists
+    pdl_wait();                                 // k_tile_prep's window table and beam lists (and k_motion's step parameters)
+    const float *__restrict__ scan = sp->scan;
     const int n_chunks = tw->n_chunks;
     const int dbg = g_staged_dbg;
     const bool stamp = (dbg & 16) && tid == 0 && blockIdx.x < 256;

@@ -497,14 +497,14 @@ k_score_tiled(const __grid_constant__ CUtensorMap tmap, const int8_t *__restrict
               const TiledWork *__restrict__ tw, const float4 *__restrict__ pcs, int *__restrict__ acc_row, int *__restrict__ counters)
 {
     TraceScope trace_scope(kTrScore);
-    const float *__restrict__ scan = sp->scan;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
     // the gather copy of the window is STATIC shared memory: its address is a link-time constant, so the gather's LDS
     // carries it as an immediate and the loop needs no base add
     __shared__ __align__(16) int8_t s_skew[kSkewBytes];
     const int tid = threadIdx.x;
-    pdl_wait();                                 // k_tile_prep's window table
+    pdl_wait();                                 // k_tile_prep's window table (and, before it, k_motion's step parameters)
+    const float *__restrict__ scan = sp->scan;
     const int n_chunks = tw->n_chunks;
 
     // the frame's window table and work prefix into shared memory (one parallel round of global loads;

@@ -113,15 +113,17 @@ struct pfslam_engine {
     StepParams *h_sp = nullptr;            // kParamSlots pinned slots
     StepParams cur{};                      // what the device copy will hold once the stream drains
     unsigned long long n_param_pushes = 0;
+    bool cur_valid = false;        // `cur` is what the device StepParams hold (or will, in stream order)
     cudaEvent_t lap_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
-    cudaGraphNode_t graph_param_node = nullptr;
+    cudaGraphNode_t graph_param_node = nullptr;      // the k_motion kernel node: the step's parameters are its last argument
     // the same step with the host API's copies inside: scan H2D from the pinned staging buffer at the head,
     // frame result D2H into pinned memory at the tail (pfslam_step = one launch + one synchronisation)
     cudaGraph_t graph_io = nullptr;
     cudaGraphExec_t graph_io_exec = nullptr;
     cudaGraphNode_t graph_io_param_node = nullptr;
+    StepParams capture_params = {};                   // k_motion's by-value argument while a step graph is being captured
     bool graph_failed = false;
     bool use_graph = true;
     int graph_kernels = 0, graph_io_kernels = 0;
@@ -174,13 +176,13 @@ static int param_slot_used(pfslam_engine *e)
 static int push_params(pfslam_engine *e, const float *scan, int frame)
 {
     if (e->in_capture || e->external_params) return PFSLAM_OK;   // a graph's copy node / the host does it
-    if (e->cur.scan == scan && e->cur.frame == frame && e->cur.seq == e->seq && e->n_param_pushes) return PFSLAM_OK;
+    if (e->cur.scan == scan && e->cur.frame == frame && e->cur.seq == e->seq && e->cur_valid) return PFSLAM_OK;
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
     if (rc) return rc;
     slot->scan = scan; slot->frame = frame; slot->seq = e->seq; slot->scan_src = nullptr; slot->res_host = nullptr;
     CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
-    e->cur = *slot;
+    e->cur = *slot; e->cur_valid = true;
     return param_slot_used(e);
 }
 
@@ -499,7 +501,7 @@ int pfslam_set_params(pfslam_engine *e, const float *scan_dev, int32_t frame)
     if (rc) return rc;
     slot->scan = scan_dev ? scan_dev : e->scan; slot->frame = frame; slot->seq = e->seq; slot->scan_src = nullptr; slot->res_host = nullptr;
     CUDA_TRY(cudaMemcpyAsync(e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice, e->stream));
-    e->cur = *slot;
+    e->cur = *slot; e->cur_valid = true;
     return param_slot_used(e);
 }
 
@@ -622,6 +624,16 @@ static int push_snapshot(pfslam_engine *e, cudaStream_t st)
     return PFSLAM_OK;
 }
 
+// k_motion's by-value copy of the step parameters: real values inside a step graph (the launch updates the node's
+// argument), "look in device memory" everywhere else (push_params / the host has put them there)
+static StepParams motion_params(pfslam_engine *e)
+{
+    if (e->in_capture) return e->capture_params;
+    StepParams p = {};
+    p.seq = kParamsInDeviceMemory;
+    return p;
+}
+
 static int ph_motion(pfslam_engine *e, int32_t frame)
 {
     { int rc = push_params(e, e->cur.scan ? e->cur.scan : e->scan, frame); if (rc) return rc; }
@@ -629,7 +641,8 @@ static int ph_motion(pfslam_engine *e, int32_t frame)
     // the pre-resample snapshot is written by the same kernel (hosts that all-gather it pass none)
     k_motion<<<ceil_div(e->n, 256), 256, 0, e->stream>>>(e->x, e->y, e->th, e->n, e->sp, e->gidx0, e->twork->bounds,
                                                          xc.snap, xc.snap_stride, xc.parity_mask, xc.snap_aos, e->score_partial,
-                                                         e->io_capture ? e->h_scan_dev : nullptr, e->scan, e->cfg.n_beams, e->pcs);
+                                                         e->io_capture ? e->h_scan_dev : nullptr, e->scan, e->cfg.n_beams, e->pcs,
+                                                         motion_params(e));
     if (e->laps_on) e->laps.mark(e->stream, kLapMotion);
     e->bounds_valid = true;
     e->launches++;
@@ -1101,7 +1114,8 @@ static int build_graph(pfslam_engine *e, bool with_io)
 {
     const long long launches_before = e->launches;
     if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return -1; }
-    cudaMemcpyAsync(e->sp, &e->h_sp[0], sizeof(StepParams), cudaMemcpyHostToDevice, e->stream);
+    e->capture_params = StepParams{};                    // placeholder: every launch sets the node's argument
+    e->capture_params.scan = e->scan;
     e->in_capture = true; e->io_capture = with_io;       // with_io: k_motion pulls the scan from the mapped staging buffer
     int rc = run_phases(e, nullptr, 0);
     e->in_capture = false; e->io_capture = false;
@@ -1119,10 +1133,10 @@ static int build_graph(pfslam_engine *e, bool with_io)
     for (auto nd : nodes) {
         cudaGraphNodeType ty;
         cudaGraphNodeGetType(nd, &ty);
-        if (ty == cudaGraphNodeTypeKernel) n_kernels++;
-        if (ty == cudaGraphNodeTypeMemcpy) {
-            cudaMemcpy3DParms mp;
-            if (cudaGraphMemcpyNodeGetParams(nd, &mp) == cudaSuccess && mp.dstPtr.ptr == (void *)e->sp) pn = nd;
+        if (ty == cudaGraphNodeTypeKernel) {
+            n_kernels++;
+            cudaKernelNodeParams kp;
+            if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == (void *)k_motion && kp.kernelParams) pn = nd;
         }
     }
     if (!pn) { cudaGraphDestroy(g); return -1; }
@@ -1140,19 +1154,25 @@ static bool graph_usable(const pfslam_engine *e)
 
 // one replay of a captured step with this frame's parameters in its head copy node; io_slot >= 0: the slot of the pinned
 // scan / result rings the step pulls its scan from and publishes its result into
+constexpr int kMotionArgs = 17;       // k_motion's parameter count; the by-value StepParams is the last one
 static int launch_graph(pfslam_engine *e, cudaGraphExec_t ge, cudaGraphNode_t pn, const float *scan, int32_t frame, int io_slot = -1)
 {
-    StepParams *slot = nullptr;
-    int rc = next_param_slot(e, &slot);
-    if (rc) return rc;
-    slot->scan = scan; slot->frame = frame; slot->seq = e->seq;
-    slot->scan_src = io_slot >= 0 ? e->h_scan_dev + (size_t)io_slot * e->cfg.n_beams : nullptr;
-    slot->res_host = io_slot >= 0 ? e->h_res_dev + io_slot : nullptr;
-    CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ge, pn, e->sp, slot, sizeof(StepParams), cudaMemcpyHostToDevice));
+    StepParams p;
+    p.scan = scan; p.frame = frame; p.seq = e->seq;
+    p.scan_src = io_slot >= 0 ? e->h_scan_dev + (size_t)io_slot * e->cfg.n_beams : nullptr;
+    p.res_host = io_slot >= 0 ? e->h_res_dev + io_slot : nullptr;
+    // the parameters are the last argument of the graph's k_motion node (copied by the call: nothing to keep alive)
+    cudaKernelNodeParams kp;
+    CUDA_TRY(cudaGraphKernelNodeGetParams(pn, &kp));
+    void *args[kMotionArgs];
+    for (int i = 0; i < kMotionArgs - 1; i++) args[i] = kp.kernelParams[i];
+    args[kMotionArgs - 1] = &p;
+    kp.kernelParams = args;
+    CUDA_TRY(cudaGraphExecKernelNodeSetParams(ge, pn, &kp));
     CUDA_TRY(cudaGraphLaunch(ge, e->stream));
-    e->cur = *slot;
+    e->cur = p; e->cur_valid = true;
     e->launches += ge == e->graph_io_exec ? e->graph_io_kernels : e->graph_kernels;
-    return param_slot_used(e);
+    return PFSLAM_OK;
 }
 
 int pfslam_step_async(pfslam_engine *e, const float *scan_dev, int32_t frame)
