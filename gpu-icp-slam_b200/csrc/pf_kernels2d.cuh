@@ -126,7 +126,7 @@ struct FrameResult {
 };
 
 // per-step inputs, read by the kernels from device memory so that a captured CUDA graph of the
-// step can be replayed with new values (a 16-byte H2D copy node at the head of the graph)
+// step can be replayed with new values (k_motion, the step's first kernel, receives them by value and files them here)
 struct FrameResult;
 constexpr int kParamsInDeviceMemory = (int)0x80000000;    // StepParams.seq of a by-value argument that is not one
 struct StepParams {

@@ -175,7 +175,7 @@ static int param_slot_used(pfslam_engine *e)
 // make the device StepParams equal (scan, frame) for the kernels enqueued after this call
 static int push_params(pfslam_engine *e, const float *scan, int frame)
 {
-    if (e->in_capture || e->external_params) return PFSLAM_OK;   // a graph's copy node / the host does it
+    if (e->in_capture || e->external_params) return PFSLAM_OK;   // the graph's k_motion argument / the host does it
     if (e->cur.scan == scan && e->cur.frame == frame && e->cur.seq == e->seq && e->cur_valid) return PFSLAM_OK;
     StepParams *slot = nullptr;
     int rc = next_param_slot(e, &slot);
@@ -1108,8 +1108,8 @@ static int run_phases(pfslam_engine *e, const float *scan_dev, int32_t frame)
     return PFSLAM_OK;
 }
 
-// Capture the whole single-GPU step once; every later step is one cudaGraphLaunch whose head node
-// copies that step's {scan pointer, frame} from a pinned slot into the device StepParams.
+// Capture the whole single-GPU step once; every later step is one cudaGraphLaunch, with that step's {scan pointer,
+// frame, sequence number, I/O slots} set as the last argument of the graph's first kernel node (k_motion) beforehand.
 static int build_graph(pfslam_engine *e, bool with_io)
 {
     const long long launches_before = e->launches;
@@ -1152,7 +1152,7 @@ static bool graph_usable(const pfslam_engine *e)
     return e->use_graph && !e->prof_on && !e->laps_on && !e->graph_failed && e->cfg.path == PFSLAM_PATH_GRID2D;
 }
 
-// one replay of a captured step with this frame's parameters in its head copy node; io_slot >= 0: the slot of the pinned
+// one replay of a captured step with this frame's parameters in its k_motion node; io_slot >= 0: the slot of the pinned
 // scan / result rings the step pulls its scan from and publishes its result into
 constexpr int kMotionArgs = 17;       // k_motion's parameter count; the by-value StepParams is the last one
 static int launch_graph(pfslam_engine *e, cudaGraphExec_t ge, cudaGraphNode_t pn, const float *scan, int32_t frame, int io_slot = -1)
