@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -185,6 +186,13 @@ static int push_params(pfslam_engine *e, const float *scan, int frame)
     e->cur = *slot; e->cur_valid = true;
     return param_slot_used(e);
 }
+
+constexpr int kMotionArgs = 17;       // k_motion's parameter count; the by-value StepParams is the last one
+template <class... A> constexpr int kernel_arity(void (*)(A...)) { return (int)sizeof...(A); }
+template <class R, class... A> struct last_arg { using type = typename last_arg<A...>::type; };
+template <class R> struct last_arg<R> { using type = R; };
+template <class... A> constexpr bool ends_in_step_params(void (*)(A...)) { return std::is_same<typename last_arg<A...>::type, const StepParams>::value || std::is_same<typename last_arg<A...>::type, StepParams>::value; }
+static_assert(kernel_arity(k_motion) == kMotionArgs && ends_in_step_params(k_motion), "launch_graph patches k_motion's last argument");
 
 extern "C" {
 
@@ -1154,7 +1162,6 @@ static bool graph_usable(const pfslam_engine *e)
 
 // one replay of a captured step with this frame's parameters in its k_motion node; io_slot >= 0: the slot of the pinned
 // scan / result rings the step pulls its scan from and publishes its result into
-constexpr int kMotionArgs = 17;       // k_motion's parameter count; the by-value StepParams is the last one
 static int launch_graph(pfslam_engine *e, cudaGraphExec_t ge, cudaGraphNode_t pn, const float *scan, int32_t frame, int io_slot = -1)
 {
     StepParams p;

@@ -145,3 +145,62 @@ def test_scene_parser_matches_reference():
     m = Scene(path).maps[0]
     got = np.array(list(m["scale"]) + list(m["resolution"]), np.float32)
     assert np.array_equal(got, G["scene_map"])
+
+
+def _ray_cells_by_ring(cx, cy, ex, ey, w, h):
+    """cells of traceRay(cx, cy -> ex, ey) in closed form, keyed by ring = distance from (cx, cy) along the major axis
+    (what k_map_free's free_ray / free_ray_cell compute); -1 where the step leaves the map"""
+    a, b, c, d = cx, cy, ex, ey
+    steep = abs(d - b) > abs(c - a)
+    if steep:
+        a, b, c, d = b, a, d, c
+    swapped = a > c
+    if swapped:
+        a, b, c, d = c, d, a, b
+    dx, dy, e0 = c - a, abs(d - b), (c - a) // 2
+    ystep = 1 if d > b else -1
+    k = np.arange(dx)
+    num = k * dy - e0
+    mk = np.where(num > 0, (num + dx - 1) // max(dx, 1), 0)
+    xx, yy = a + k, b + ystep * mk
+    idx = np.where(steep, yy * w + xx, xx * w + yy)
+    ok = (xx < w) & (yy < h) & (xx >= 0) & (yy >= 0) & (idx < w * h)
+    ring = (dx - k) if swapped else k
+    return dict(zip(ring.tolist(), np.where(ok, idx, -1).tolist()))
+
+
+def test_adjacent_beam_skip_rule_loses_no_cell(oracle):
+    """k_map_free skips a step when the PREVIOUS beam visits the same cell at the same ring (so the lowest beam of a run
+    of coinciding rays claims it).  Property: the cells of the kept steps are exactly the cells of all steps, = the
+    union of the oracle's sequential traceRay over the fan -- for fans with dropped (out-of-range) beams, a centre near
+    the map border, and rays that cross the steep / swapped boundaries."""
+    rng = np.random.default_rng(11)
+    w = h = 1600
+    for case in range(6):
+        cx, cy = (rng.integers(300, 1300, 2) if case < 4 else rng.integers(0, 60, 2))
+        theta = rng.uniform(-3.2, 3.2)
+        ang = theta + np.deg2rad(-135.0 + 0.25 * np.arange(1081))
+        r = rng.uniform(0.3, 19.0) + np.cumsum(rng.normal(0, 0.05, 1081))      # a wall-like range profile
+        r[rng.random(1081) < 0.1] = 30.0                                        # beams that fail the +-20 m filter
+        valid = (np.abs(r * np.cos(ang)) < 20.0) & (np.abs(r * np.sin(ang)) < 20.0)
+        ex = (np.round(r * np.cos(ang) / 0.025) + cx).astype(int)
+        ey = (np.round(r * np.sin(ang) / 0.025) + cy).astype(int)
+        want = np.zeros(w * h, np.uint8)
+        kept, total = set(), 0
+        prev = None
+        for j in range(1081):
+            cur = _ray_cells_by_ring(int(cx), int(cy), int(ex[j]), int(ey[j]), w, h) if valid[j] else None
+            if cur is not None:
+                oracle.pfo_trace_ray(int(cx), int(cy), int(ex[j]), int(ey[j]), w, h, P(want, helpers.ubp))
+                for ring, cell in cur.items():
+                    if cell < 0:
+                        continue
+                    total += 1
+                    if prev is not None and prev.get(ring, -1) == cell:
+                        continue                                   # the previous beam has it
+                    kept.add(cell)
+            prev = cur
+        got = np.zeros(w * h, np.uint8)
+        got[list(kept)] = 1
+        assert np.array_equal(got, want), "case %d" % case
+        assert len(kept) <= total
